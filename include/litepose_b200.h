@@ -1,0 +1,158 @@
+/*
+ * litepose_b200 -- C ABI of the B200 (sm_100a) LitePose inference kernels.
+ *
+ * The reference (mit-han-lab/litepose) is a pure Python/PyTorch project; its hot
+ * path has no FFI of its own.  This header is the boundary a maintainer binds
+ * with ctypes to replace, function by function:
+ *
+ *   lp_stem_*            <- LitePose.first            lib/models/pose_mobilenet.py:36-41
+ *   lp_pw1x1_* / lp_dwconv_*
+ *                        <- InvBottleneck.forward     lib/models/layers/layers.py:90-118
+ *   lp_fusion_deconv_*   <- deconv_refined/raw + BN + ReLU
+ *                                                     lib/models/pose_mobilenet.py:102-135,146-149
+ *   lp_head_*            <- final_refined/final_raw (SepConv2d)
+ *                                                     lib/models/pose_mobilenet.py:86-100,151-154
+ *                                                     lib/models/layers/layers.py:120-133
+ *   lp_nms_topk_*        <- HeatmapParser.nms/top_k   lib/core/group.py:131-176
+ *   lp_tag_match_*       <- match_by_tag/py_max_match lib/core/group.py:19-97
+ *   lp_adjust_refine_*   <- HeatmapParser.adjust/refine + scores
+ *                                                     lib/core/group.py:178-291
+ *   lp_glue_*            <- get_multi_stage_outputs/aggregate_results
+ *                                                     lib/core/inference.py:75-208
+ *
+ * Conventions (modelled on the reference's own native plugin convention,
+ * nano_demo/fast_utils/plugins.cpp: caller-allocated *_out buffers, raw pointers):
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter is documented as host memory (weight packing helpers);
+ *   - the caller owns all inputs, outputs and workspaces; the library never
+ *     allocates device memory, never frees and never retains a pointer;
+ *   - work is enqueued on `stream` (a cudaStream_t); no hidden synchronisation;
+ *   - every entry point returns LP_OK or an error code, never aborts;
+ *     lp_last_error() gives a thread-local message for the last failure;
+ *   - activations are NHWC fp16 between kernels; the stem reads the reference's
+ *     NCHW input, the heads write the reference's NCHW fp32 outputs;
+ *   - re-entrant per device/stream: no unguarded global state.
+ */
+#ifndef LITEPOSE_B200_H
+#define LITEPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lp_stream_t; /* cudaStream_t */
+
+enum {
+    LP_OK = 0,
+    LP_ERR_BAD_ARG = 1,   /* shape / value out of the supported range */
+    LP_ERR_ALIGN = 2,     /* pointer or stride not sufficiently aligned */
+    LP_ERR_ARCH = 3,      /* device is not sm_100 */
+    LP_ERR_CUDA = 4,      /* CUDA runtime / driver failure (launch, tensor map ...) */
+    LP_ERR_CAPACITY = 5   /* workspace or output capacity too small */
+};
+
+enum { LP_ACT_NONE = 0, LP_ACT_RELU = 1, LP_ACT_RELU6 = 2 };
+
+/* ---- library state ------------------------------------------------------ */
+int lp_version(void);
+const char* lp_last_error(void);
+/* LP_OK iff the current device is compute capability 10.x */
+int lp_device_check(void);
+/* number of kernels this library launched (process-wide counter) */
+uint64_t lp_launch_count(void);
+void lp_reset_launch_count(void);
+
+/* ---- M1: stem conv3x3 stride 2 (3 -> 32) + bias + ReLU6 ------------------
+ * x: NCHW [N,3,H,W], fp32 (x_is_fp32 != 0) or fp16;  w: fp16 [32][27] (co, ci*9+ky*3+kx)
+ * BN-folded;  bias: fp32 [32];  y: NHWC fp16 [N,H/2,W/2,32].  H, W even.
+ * flip_x != 0 reads the image mirrored along W, i.e. computes the stem of
+ * torch.flip(x, [3]) (the flip-test pass, lib/core/inference.py:120) without a copy. */
+int lp_stem_conv3x3_s2(const void* x, int x_is_fp32, int flip_x, const void* w, const float* bias,
+                       void* y, int N, int H, int W, lp_stream_t stream);
+
+/* ---- M1/M2/M4: depthwise k x k (k in {3,5,7}), stride 1|2, pad k/2 ---------
+ * x: NHWC fp16 [N,H,W,C];  w: fp16 [k*k][C] (tap-major, BN-folded);  bias fp32 [C];
+ * y: NHWC fp16 [N,H/stride,W/stride,C].  C % 8 == 0; H, W even when stride == 2. */
+int lp_dwconv_f16(const void* x, const void* w, const float* bias, void* y, int N, int C, int H,
+                  int W, int k, int stride, int act, lp_stream_t stream);
+
+/* ---- M1/M2: pointwise 1x1 as tcgen05 GEMM ---------------------------------
+ * out[M,N] = act(a[M,K] * W^T + bias) (+ residual[M,N]);  a/out/residual fp16 row-major
+ * (NHWC activations flattened, M = batch*H*W);  K % 8 == 0, N % 8 == 0.
+ * Weights must be packed once (host memory in, host memory out): */
+size_t lp_pw1x1_packed_elems(int K, int N);        /* fp16 elements */
+size_t lp_pw1x1_packed_bias_elems(int N);          /* fp32 elements */
+int lp_pw1x1_pack(const uint16_t* w_f16 /*[N][K] host*/, const float* bias /*[N] host or NULL*/,
+                  int K, int N, uint16_t* w_packed /*host*/, float* bias_packed /*host*/);
+int lp_pw1x1_f16(const void* a, const void* w_packed, const float* bias_packed, const void* residual,
+                 void* out, int M, int K, int N, int act, lp_stream_t stream);
+
+/* ---- M3: fusion deconv level ----------------------------------------------
+ * out = ReLU(ConvT4x4s2p1(refined) + ConvT4x4s2p1(raw) + bias), one kernel.
+ * refined NHWC fp16 [N,H,W,Cr], raw [N,H,W,Cw], out [N,2H,2W,Co].
+ * w_refined/w_raw: BN-scaled fp16 in the reference layout [Cin][Co][4][4] (host). */
+size_t lp_deconv_packed_elems(int Cr, int Cw, int Co);
+size_t lp_deconv_packed_bias_elems(int Co);
+int lp_deconv_pack(const uint16_t* w_refined, const uint16_t* w_raw, const float* bias, int Cr, int Cw,
+                   int Co, uint16_t* w_packed, float* bias_packed);
+int lp_fusion_deconv_f16(const void* refined, const void* raw, const void* w_packed,
+                         const float* bias_packed, void* out, int N, int H, int W, int Cr, int Cw,
+                         int Co, lp_stream_t stream);
+
+/* ---- M4: head pointwise pair ------------------------------------------------
+ * out_nchw[N,Co,H,W] = a1[N,H,W,C1] * W1^T + a2[N,H,W,C2] * W2^T  (no bias, no act);
+ * out is fp32 (out_fp32 != 0; what the reference hands to the glue after tofp32) or fp16;
+ * a1/a2 are the ReLU'd depthwise-5x5 outputs (lp_dwconv_f16).  w1 [Co][C1], w2 [Co][C2] host fp16. */
+size_t lp_head_packed_elems(int C1, int C2, int Co);
+int lp_head_pack(const uint16_t* w1, const uint16_t* w2, int C1, int C2, int Co, uint16_t* w_packed);
+int lp_head_pw_dual_f16(const void* a1, const void* a2, const void* w_packed, void* out_nchw,
+                        int out_fp32, int N, int H, int W, int C1, int C2, int Co, lp_stream_t stream);
+
+/* ---- G1+G2: NMS (k x k window max, -inf padding) + top-K per (n,j) plane -----
+ * det fp32 [N,J,H,W]; tag fp32 [N,J,H,W,T].  Order: value desc, flat index asc over
+ * NMS survivors with value > 0; unused slots are (0.0f, index 0).
+ * val_k [N,J,K] f32; ind_k [N,J,K] i32 (flat y*W+x); tag_k [N,J,K,T] f32.  K <= 64. */
+size_t lp_nms_topk_workspace_bytes(int N, int J, int H, int W, int K);
+int lp_nms_topk_f32(const float* det, const float* tag, int N, int J, int H, int W, int T,
+                    int nms_kernel, int K, float* val_k, int32_t* ind_k, float* tag_k,
+                    void* workspace, size_t workspace_bytes, lp_stream_t stream);
+
+/* ---- G3: tag matching (match_by_tag + Munkres), one image per CTA -----------
+ * joint_order: int32 [J] device.  ans [N,pcap,J,3+T] f32 (x,y,val,tags), rows in
+ * person-creation order; num_people [N] i32 (true count, may exceed pcap ->
+ * LP_ERR_CAPACITY is NOT raised on the device; the caller compares against pcap;
+ * pcap = J*K can never overflow).  Thresholds are doubles because the reference
+ * compares float64 joint rows against Python floats (group.py:38-41,84). */
+size_t lp_tag_match_workspace_bytes(int N, int J, int K, int T, int pcap);
+int lp_tag_match_f32(const float* val_k, const int32_t* ind_k, const float* tag_k, int N, int J,
+                     int K, int T, int W, const int32_t* joint_order, double det_threshold,
+                     double tag_threshold, int use_detection_val, int ignore_too_much,
+                     int max_num_people, int pcap, float* ans, int32_t* num_people,
+                     void* workspace, size_t workspace_bytes, lp_stream_t stream);
+
+/* ---- G4+G5+G6: adjust, scores, refine ---------------------------------------
+ * In-place on ans [N,pcap,J,3+T]; scores [N,pcap] f32 = mean joint value after adjust
+ * and before refine (group.py:275).  det/tag as for lp_nms_topk_f32 (un-NMS'd det). */
+size_t lp_adjust_refine_workspace_bytes(int N, int J, int pcap);
+int lp_adjust_refine_f32(const float* det, const float* tag, int N, int J, int H, int W, int T,
+                         int pcap, float* ans, const int32_t* num_people, float* scores,
+                         int do_adjust, int do_refine, void* workspace, size_t workspace_bytes,
+                         lp_stream_t stream);
+
+/* ---- glue ("next" row 1): fused flip/upsample/average/project ----------------
+ * From the two forward passes' outputs (plain: o0 [N,2J,h,w], o1 [N,J,2h,2w]; flipped
+ * pass: f0, f1, NULL when flip == 0) produce det [N,J,Hd,Wd] and tag [N,J,Hd,Wd,T]
+ * (T = 2 with flip else 1) exactly as get_multi_stage_outputs + aggregate_results do for
+ * SCALE_FACTOR [1], WITH_HEATMAPS (1,1), WITH_AE (1,0).  (Hd,Wd) == (2h,2w): no
+ * projection; otherwise PROJECT2IMAGE to size_projected = (Wd,Hd).  flip_index: int32 [J]. */
+int lp_glue_f32(const float* o0, const float* o1, const float* f0, const float* f1,
+                const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd, int Wd,
+                float* det, float* tag, lp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITEPOSE_B200_H */

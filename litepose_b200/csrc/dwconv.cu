@@ -1,0 +1,170 @@
+// Depthwise k x k convolution (+ folded-BN bias + activation), NHWC fp16, sm_100a.
+// Reference op: nn.Conv2d(C, C, k, stride, k//2, groups=C) + BatchNorm2d + ReLU6/ReLU
+//   (reference lib/models/layers/layers.py:100-104 depth_conv k=7; :123-127 SepConv2d k=5;
+//    lib/models/pose_mobilenet.py:38 stem dw3x3).
+//
+// HBM-bound design: one CTA owns a (TH x TW) output tile of a 32-channel slab.  The haloed
+// input tile is staged in shared memory by ONE TMA tensor copy (cp.async.bulk.tensor.4d) whose
+// out-of-bounds zero fill implements the conv padding and every image/channel border, so the
+// compute loop has no boundary branches.  Each thread owns one channel PAIR (half2) and walks
+// 4x4 output micro-blocks with the k*k half2 weights held in registers, accumulating in fp32.
+// Algorithmic bytes per launch: 2*(N*C*Hin*Win + N*C*Hout*Wout + C*k*k) (+4*C bias).
+#include "common.cuh"
+
+namespace lp {
+
+constexpr int DW_CB = 32;        // channels per CTA slab
+constexpr int DW_THREADS = 256;  // 16 channel pairs x 16 micro-block slots
+constexpr int BY = 4, BX = 4;    // outputs per thread micro-block
+
+template <int K, int S>
+struct DwCfg {
+    static constexpr int TH = (S == 1) ? 32 : 16;          // output tile
+    static constexpr int TW = (S == 1) ? 32 : 16;
+    static constexpr int IH = (TH - 1) * S + K;             // input tile incl. halo
+    static constexpr int IW = (TW - 1) * S + K;
+    static constexpr int IR = (BY - 1) * S + K;             // input rows / cols per micro-block
+    static constexpr int IC = (BX - 1) * S + K;
+    static constexpr int SMEM = IH * IW * DW_CB * 2 + 128 + 64;
+};
+
+template <int K, int S>
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict__ w, const float* __restrict__ bias,
+              __half* __restrict__ y, int C, int Hout, int Wout, int tiles_x, int act) {
+    using Cfg = DwCfg<K, S>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Cfg::IH * Cfg::IW * DW_CB * 2);
+
+    const int tile = blockIdx.x;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int c0 = blockIdx.y * DW_CB;
+    const int n = blockIdx.z;
+    const int ox0 = tx * Cfg::TW, oy0 = ty * Cfg::TH;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, Cfg::IH * Cfg::IW * DW_CB * 2);
+        tma_load_4d(smem, &map_x, bar, c0, ox0 * S - K / 2, oy0 * S - K / 2, n);
+    }
+
+    const int cp = threadIdx.x & 15;       // channel pair inside the slab
+    const int slot = threadIdx.x >> 4;     // 16 micro-block slots
+    const int ch = c0 + 2 * cp;
+    const bool ch_ok = ch < C;
+
+    // weights for this channel pair: tap-major [k*k][C]
+    __half2 wreg[K * K];
+#pragma unroll
+    for (int t = 0; t < K * K; ++t)
+        wreg[t] = ch_ok ? *reinterpret_cast<const __half2*>(w + (size_t)t * C + ch) : __floats2half2_rn(0.f, 0.f);
+    float2 b2 = make_float2(0.f, 0.f);
+    if (ch_ok && bias) b2 = make_float2(bias[ch], bias[ch + 1]);
+
+    __syncthreads();          // barrier init visible to all waiters
+    mbar_wait(bar, 0);
+
+    const __half2* tile_in = reinterpret_cast<const __half2*>(smem);   // [IH][IW][16 pairs]
+    constexpr int BLOCKS_X = Cfg::TW / BX;
+    constexpr int NBLOCKS = (Cfg::TH / BY) * BLOCKS_X;
+
+#pragma unroll 1
+    for (int blk = slot; blk < NBLOCKS; blk += 16) {
+        const int by = blk / BLOCKS_X, bx = blk % BLOCKS_X;
+        const int oy = by * BY, ox = bx * BX;           // tile-local output origin
+        if (oy0 + oy >= Hout || ox0 + ox >= Wout) continue;   // micro-block fully outside
+        float2 acc[BY][BX];
+#pragma unroll
+        for (int i = 0; i < BY; ++i)
+#pragma unroll
+            for (int j = 0; j < BX; ++j) acc[i][j] = b2;
+
+        const __half2* base = tile_in + ((oy * S) * Cfg::IW + ox * S) * (DW_CB / 2) + cp;
+#pragma unroll
+        for (int r = 0; r < Cfg::IR; ++r) {
+            float2 in[Cfg::IC];
+#pragma unroll
+            for (int c = 0; c < Cfg::IC; ++c) in[c] = __half22float2(base[(r * Cfg::IW + c) * (DW_CB / 2)]);
+#pragma unroll
+            for (int i = 0; i < BY; ++i) {
+                const int ky = r - i * S;
+                if (ky >= 0 && ky < K) {
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx) {
+                        const float2 wf = __half22float2(wreg[ky * K + kx]);
+#pragma unroll
+                        for (int j = 0; j < BX; ++j) {
+                            acc[i][j].x = fmaf(in[j * S + kx].x, wf.x, acc[i][j].x);
+                            acc[i][j].y = fmaf(in[j * S + kx].y, wf.y, acc[i][j].y);
+                        }
+                    }
+                }
+            }
+        }
+        if (ch_ok) {
+#pragma unroll
+            for (int i = 0; i < BY; ++i) {
+                const int gy = oy0 + oy + i;
+                if (gy >= Hout) continue;
+#pragma unroll
+                for (int j = 0; j < BX; ++j) {
+                    const int gx = ox0 + ox + j;
+                    if (gx >= Wout) continue;
+                    const float vx = act_apply(acc[i][j].x, act), vy = act_apply(acc[i][j].y, act);
+                    *reinterpret_cast<__half2*>(y + (((size_t)n * Hout + gy) * Wout + gx) * C + ch) =
+                        __floats2half2_rn(vx, vy);
+                }
+            }
+        }
+    }
+}
+
+template <int K, int S>
+static int launch_dw(const void* x, const void* w, const float* bias, void* y, int N, int C, int H, int W, int act,
+                     cudaStream_t stream) {
+    using Cfg = DwCfg<K, S>;
+    const int Hout = H / S, Wout = W / S;
+    CUtensorMap map;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {(uint32_t)DW_CB, (uint32_t)Cfg::IW, (uint32_t)Cfg::IH, 1u};
+    int rc = make_tmap(&map, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute((const void*)dwconv_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dwconv)");
+    const int tiles_x = (Wout + Cfg::TW - 1) / Cfg::TW, tiles_y = (Hout + Cfg::TH - 1) / Cfg::TH;
+    dim3 grid(tiles_x * tiles_y, (C + DW_CB - 1) / DW_CB, N);
+    dwconv_kernel<K, S><<<grid, DW_THREADS, Cfg::SMEM, stream>>>(map, reinterpret_cast<const __half*>(w), bias,
+                                                                 reinterpret_cast<__half*>(y), C, Hout, Wout, tiles_x,
+                                                                 act);
+    LP_LAUNCH_CHECK("dwconv_kernel");
+    return LP_OK;
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+extern "C" int lp_dwconv_f16(const void* x, const void* w, const float* bias, void* y, int N, int C, int H, int W, int k,
+                             int stride, int act, lp_stream_t stream) {
+    LP_CHECK_ARG(x && w && y, "lp_dwconv_f16: null pointer");
+    LP_CHECK_ARG(N > 0 && N <= 65535 && C > 0 && C % 8 == 0 && H > 0 && W > 0,
+                 "lp_dwconv_f16: bad shape N=%d C=%d H=%d W=%d", N, C, H, W);
+    LP_CHECK_ARG((k == 3 || k == 5 || k == 7) && (stride == 1 || stride == 2), "lp_dwconv_f16: k=%d stride=%d unsupported",
+                 k, stride);
+    LP_CHECK_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0), "lp_dwconv_f16: stride 2 needs even H, W (%d, %d)", H, W);
+    LP_CHECK_ARG(act >= LP_ACT_NONE && act <= LP_ACT_RELU6, "lp_dwconv_f16: bad act %d", act);
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 3) || (reinterpret_cast<uintptr_t>(w) & 3)) {
+        set_error("lp_dwconv_f16: x must be 16-byte aligned, w/y 4-byte aligned");
+        return LP_ERR_ALIGN;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k == 7 && stride == 1) return launch_dw<7, 1>(x, w, bias, y, N, C, H, W, act, s);
+    if (k == 7 && stride == 2) return launch_dw<7, 2>(x, w, bias, y, N, C, H, W, act, s);
+    if (k == 5 && stride == 1) return launch_dw<5, 1>(x, w, bias, y, N, C, H, W, act, s);
+    if (k == 5 && stride == 2) return launch_dw<5, 2>(x, w, bias, y, N, C, H, W, act, s);
+    if (k == 3 && stride == 1) return launch_dw<3, 1>(x, w, bias, y, N, C, H, W, act, s);
+    return launch_dw<3, 2>(x, w, bias, y, N, C, H, W, act, s);
+}

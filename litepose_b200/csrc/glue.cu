@@ -1,0 +1,161 @@
+// Fused test-time glue between model and parser ("next" row 1 of SURVEY.md §8f).
+// Reference: get_multi_stage_outputs + aggregate_results, lib/core/inference.py:75-208, for the evaluation
+// configuration of record (SCALE_FACTOR [1], LOSS.WITH_HEATMAPS_LOSS (1,1), TEST.WITH_HEATMAPS (1,1),
+// WITH_AE (1,0), TAG_PER_JOINT):
+//   plain pass : u0 = bilinear(o0 -> size of o1); ha = (u0[:J] + o1) / 2 ; t0 = u0[J:]
+//   flip pass  : uf = flip_x(bilinear(f0)), g1 = flip_x(f1); hf = (uf[:J][fidx] + g1[fidx]) / 2 ; t1 = uf[J:][fidx]
+//   project    : each of ha, hf, t0, t1 -> bilinear to (Hd, Wd)   (PROJECT2IMAGE; identity when Hd,Wd == 2h,2w)
+//   aggregate  : det = (ha + hf) / 2 (or ha when no flip) ; tag = stack(t0, t1) on the last dim
+// The eager reference materialises ~10 full-resolution intermediates; this kernel reads the four model outputs once
+// (through L1/L2) and writes det/tag once: algorithmic bytes 4*N*J*(Hd*Wd*(1+T)) written + 4*N*(3J*h*w*5)*passes read.
+// Bilinear follows ATen's align_corners=False rule: src = (dst+0.5)*in/out - 0.5 clamped at 0, i1 = min(i0+1, in-1).
+#include "common.cuh"
+
+namespace lp {
+
+constexpr int GL_TO = 64;          // output tile side
+constexpr int GL_TM = 40;          // max mid-level tile side kept in shared memory
+constexpr int GL_THREADS = 256;
+
+struct Lerp {
+    int i0, i1;
+    float l0, l1;
+};
+
+__device__ __forceinline__ Lerp lerp_coord(int dst, float scale, int in_size) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    Lerp r;
+    r.i0 = min((int)src, in_size - 1);
+    r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+    r.l1 = src - (float)r.i0;
+    r.l0 = 1.f - r.l1;
+    return r;
+}
+
+__device__ __forceinline__ float bilerp(const float* __restrict__ p, int W, const Lerp& y, const Lerp& x) {
+    return y.l0 * (x.l0 * __ldg(p + y.i0 * W + x.i0) + x.l1 * __ldg(p + y.i0 * W + x.i1)) +
+           y.l1 * (x.l0 * __ldg(p + y.i1 * W + x.i0) + x.l1 * __ldg(p + y.i1 * W + x.i1));
+}
+
+__global__ void __launch_bounds__(GL_THREADS)
+glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const float* __restrict__ f0,
+            const float* __restrict__ f1, const int32_t* __restrict__ flip_index, int J, int h, int w, int flip, int Hd,
+            int Wd, int tiles_x, float* __restrict__ det, float* __restrict__ tag) {
+    __shared__ float s_ha[GL_TM][GL_TM + 1], s_hf[GL_TM][GL_TM + 1], s_t0[GL_TM][GL_TM + 1], s_t1[GL_TM][GL_TM + 1];
+    const int n = blockIdx.z, j = blockIdx.y;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int H2 = 2 * h, W2 = 2 * w;
+    const int T = flip ? 2 : 1;
+    const bool project = !(Hd == H2 && Wd == W2);
+    const float sy = (float)H2 / (float)Hd, sx = (float)W2 / (float)Wd;
+    const int oy0 = ty * GL_TO, ox0 = tx * GL_TO;
+    const int oy1 = min(oy0 + GL_TO, Hd) - 1, ox1 = min(ox0 + GL_TO, Wd) - 1;
+    // mid-level footprint of this output tile
+    int my0, my1, mx0, mx1;
+    if (project) {
+        my0 = lerp_coord(oy0, sy, H2).i0; my1 = lerp_coord(oy1, sy, H2).i1;
+        mx0 = lerp_coord(ox0, sx, W2).i0; mx1 = lerp_coord(ox1, sx, W2).i1;
+    } else {
+        my0 = oy0; my1 = oy1; mx0 = ox0; mx1 = ox1;
+    }
+    const int mh = my1 - my0 + 1, mw = mx1 - mx0 + 1;   // <= GL_TM guaranteed by the host (scale <= 0.6) unless !project
+    const float us_y = (float)h / (float)H2, us_x = (float)w / (float)W2;   // 0.5
+
+    const size_t hw = (size_t)h * w, HW2 = (size_t)H2 * W2;
+    const float* a_heat = o0 + ((size_t)n * 2 * J + j) * hw;
+    const float* a_tag = o0 + ((size_t)n * 2 * J + J + j) * hw;
+    const float* a_o1 = o1 + ((size_t)n * J + j) * HW2;
+    const float *b_heat = nullptr, *b_tag = nullptr, *b_o1 = nullptr;
+    if (flip) {
+        const int fj = flip_index[j];
+        b_heat = f0 + ((size_t)n * 2 * J + fj) * hw;
+        b_tag = f0 + ((size_t)n * 2 * J + J + fj) * hw;
+        b_o1 = f1 + ((size_t)n * J + fj) * HW2;
+    }
+
+    if (project) {
+        for (int i = threadIdx.x; i < mh * mw; i += GL_THREADS) {
+            const int ly = i / mw, lx = i - ly * mw;
+            const int y = my0 + ly, x = mx0 + lx;
+            const Lerp cy = lerp_coord(y, us_y, h), cx = lerp_coord(x, us_x, w);
+            s_ha[ly][lx] = (bilerp(a_heat, w, cy, cx) + __ldg(a_o1 + (size_t)y * W2 + x)) / 2.f;
+            s_t0[ly][lx] = bilerp(a_tag, w, cy, cx);
+            if (flip) {
+                const int xf = W2 - 1 - x;
+                const Lerp fx = lerp_coord(xf, us_x, w);
+                s_hf[ly][lx] = (bilerp(b_heat, w, cy, fx) + __ldg(b_o1 + (size_t)y * W2 + xf)) / 2.f;
+                s_t1[ly][lx] = bilerp(b_tag, w, cy, fx);
+            }
+        }
+        __syncthreads();
+    }
+
+    float* dplane = det + ((size_t)n * J + j) * Hd * Wd;
+    float* tplane = tag + ((size_t)n * J + j) * Hd * Wd * T;
+    const int th = oy1 - oy0 + 1, tw = ox1 - ox0 + 1;
+    for (int i = threadIdx.x; i < th * tw; i += GL_THREADS) {
+        const int ly = i / tw, lx = i - ly * tw;
+        const int Y = oy0 + ly, X = ox0 + lx;
+        float ha, hf = 0.f, t0, t1 = 0.f;
+        if (project) {
+            const Lerp cy = lerp_coord(Y, sy, H2), cx = lerp_coord(X, sx, W2);
+            const int y0 = cy.i0 - my0, y1 = cy.i1 - my0, x0 = cx.i0 - mx0, x1 = cx.i1 - mx0;
+#define GL_P(S) (cy.l0 * (cx.l0 * S[y0][x0] + cx.l1 * S[y0][x1]) + cy.l1 * (cx.l0 * S[y1][x0] + cx.l1 * S[y1][x1]))
+            ha = GL_P(s_ha);
+            t0 = GL_P(s_t0);
+            if (flip) {
+                hf = GL_P(s_hf);
+                t1 = GL_P(s_t1);
+            }
+#undef GL_P
+        } else {
+            const Lerp cy = lerp_coord(Y, us_y, h), cx = lerp_coord(X, us_x, w);
+            ha = (bilerp(a_heat, w, cy, cx) + __ldg(a_o1 + (size_t)Y * W2 + X)) / 2.f;
+            t0 = bilerp(a_tag, w, cy, cx);
+            if (flip) {
+                const int xf = W2 - 1 - X;
+                const Lerp fx = lerp_coord(xf, us_x, w);
+                hf = (bilerp(b_heat, w, cy, fx) + __ldg(b_o1 + (size_t)Y * W2 + xf)) / 2.f;
+                t1 = bilerp(b_tag, w, cy, fx);
+            }
+        }
+        const size_t o = (size_t)Y * Wd + X;
+        if (flip) {
+            dplane[o] = (ha + hf) / 2.f;
+            *reinterpret_cast<float2*>(tplane + o * 2) = make_float2(t0, t1);
+        } else {
+            dplane[o] = ha;
+            tplane[o] = t0;
+        }
+    }
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+extern "C" int lp_glue_f32(const float* o0, const float* o1, const float* f0, const float* f1, const int32_t* flip_index,
+                           int N, int J, int h, int w, int flip, int Hd, int Wd, float* det, float* tag,
+                           lp_stream_t stream) {
+    LP_CHECK_ARG(o0 && o1 && det && tag, "lp_glue_f32: null pointer");
+    LP_CHECK_ARG(!flip || (f0 && f1 && flip_index), "lp_glue_f32: flip pass needs f0, f1, flip_index");
+    LP_CHECK_ARG(N > 0 && N <= 65535 && J > 0 && J <= 65535 && h > 0 && w > 0 && Hd > 0 && Wd > 0,
+                 "lp_glue_f32: bad shape N=%d J=%d h=%d w=%d Hd=%d Wd=%d", N, J, h, w, Hd, Wd);
+    const bool project = !(Hd == 2 * h && Wd == 2 * w);
+    if (project) {
+        // the shared mid-level tile must cover the footprint of a 64x64 output tile
+        LP_CHECK_ARG((double)(2 * h) / Hd * GL_TO + 3 <= GL_TM && (double)(2 * w) / Wd * GL_TO + 3 <= GL_TM,
+                     "lp_glue_f32: projection must up-sample by >= 1.73x (got %dx%d -> %dx%d)", 2 * h, 2 * w, Hd, Wd);
+    }
+    if ((reinterpret_cast<uintptr_t>(tag) & 7) && flip) {
+        set_error("lp_glue_f32: tag must be 8-byte aligned");
+        return LP_ERR_ALIGN;
+    }
+    const int tiles_x = (Wd + GL_TO - 1) / GL_TO, tiles_y = (Hd + GL_TO - 1) / GL_TO;
+    dim3 grid(tiles_x * tiles_y, J, N);
+    glue_kernel<<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(o0, o1, f0, f1, flip_index, J, h, w, flip, Hd, Wd, tiles_x,
+                                                             det, tag);
+    LP_LAUNCH_CHECK("glue_kernel");
+    return LP_OK;
+}

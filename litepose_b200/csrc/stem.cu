@@ -1,0 +1,107 @@
+// Stem: conv3x3 stride 2 (3 -> 32) + folded-BN bias + ReLU6; reads the reference's NCHW input
+// (fp32, or fp16 under network_to_half) and writes the NHWC fp16 activation layout used by all
+// later kernels.  Reference: convbnrelu(3, 32, ker=3, stride=2), lib/models/pose_mobilenet.py:37,
+// lib/models/layers/layers.py:18-24.
+//
+// CTA = 32 x 8 output pixels; the 3-channel haloed input patch is staged in shared memory as
+// fp32.  Each thread computes one output pixel x 32 channels; weights are read as warp-uniform
+// float4 broadcasts from shared memory.  Output: 64 B contiguous per thread (4 x 16-byte stores).
+#include "common.cuh"
+
+namespace lp {
+
+constexpr int ST_TW = 32, ST_TH = 8;
+constexpr int ST_IW = ST_TW * 2 + 1, ST_IH = ST_TH * 2 + 1;   // 65 x 17
+constexpr int ST_IWP = ST_IW + 2;                              // pad row pitch (odd*... keeps 2-way max)
+
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+stem_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+            __half* __restrict__ y, int H, int W, int flip_x) {
+    __shared__ float s_in[3][ST_IH][ST_IWP];
+    __shared__ __align__(16) float s_w[27][32];   // [tap][co]
+    __shared__ float s_b[32];
+    const int Ho = H / 2, Wo = W / 2;
+    const int n = blockIdx.z;
+    const int ox0 = blockIdx.x * ST_TW, oy0 = blockIdx.y * ST_TH;
+    const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
+
+    for (int i = threadIdx.x; i < 27 * 32; i += 256) {
+        const int co = i & 31, t = i >> 5;
+        s_w[t][co] = __half2float(w[co * 27 + t]);
+    }
+    if (threadIdx.x < 32) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    const TIn* xn = x + (size_t)n * 3 * H * W;
+    for (int i = threadIdx.x; i < 3 * ST_IH * ST_IW; i += 256) {
+        const int c = i / (ST_IH * ST_IW);
+        const int r = (i / ST_IW) % ST_IH;
+        const int col = i % ST_IW;
+        const int gy = iy0 + r, gx = ix0 + col;
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = (float)xn[((size_t)c * H + gy) * W + (flip_x ? W - 1 - gx : gx)];
+        s_in[c][r][col] = v;
+    }
+    __syncthreads();
+
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int ox = ox0 + lx, oy = oy0 + ly;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = s_b[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float v = s_in[c][2 * ly + ky][2 * lx + kx];
+                const float4* wr = reinterpret_cast<const float4*>(s_w[c * 9 + ky * 3 + kx]);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 wv = wr[g];
+                    acc[4 * g + 0] = fmaf(v, wv.x, acc[4 * g + 0]);
+                    acc[4 * g + 1] = fmaf(v, wv.y, acc[4 * g + 1]);
+                    acc[4 * g + 2] = fmaf(v, wv.z, acc[4 * g + 2]);
+                    acc[4 * g + 3] = fmaf(v, wv.w, acc[4 * g + 3]);
+                }
+            }
+    if (ox < Wo && oy < Ho) {
+        uint4* op = reinterpret_cast<uint4*>(y + (((size_t)n * Ho + oy) * Wo + ox) * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                h[i] = __floats2half2_rn(fminf(fmaxf(acc[8 * g + 2 * i], 0.f), 6.f),
+                                         fminf(fmaxf(acc[8 * g + 2 * i + 1], 0.f), 6.f));
+            op[g] = o;
+        }
+    }
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+extern "C" int lp_stem_conv3x3_s2(const void* x, int x_is_fp32, int flip_x, const void* w, const float* bias, void* y,
+                                  int N, int H, int W, lp_stream_t stream) {
+    LP_CHECK_ARG(x && w && y, "lp_stem_conv3x3_s2: null pointer");
+    LP_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
+                 "lp_stem_conv3x3_s2: bad shape N=%d H=%d W=%d (H, W even)", N, H, W);
+    if (reinterpret_cast<uintptr_t>(y) & 15) {
+        set_error("lp_stem_conv3x3_s2: y must be 16-byte aligned");
+        return LP_ERR_ALIGN;
+    }
+    dim3 grid((W / 2 + ST_TW - 1) / ST_TW, (H / 2 + ST_TH - 1) / ST_TH, N);
+    if (x_is_fp32)
+        stem_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(x),
+                                                                  reinterpret_cast<const __half*>(w), bias,
+                                                                  reinterpret_cast<__half*>(y), H, W, flip_x);
+    else
+        stem_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(x),
+                                                                   reinterpret_cast<const __half*>(w), bias,
+                                                                   reinterpret_cast<__half*>(y), H, W, flip_x);
+    LP_LAUNCH_CHECK("stem_kernel");
+    return LP_OK;
+}

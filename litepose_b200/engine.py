@@ -1,0 +1,266 @@
+"""Host-side executor of the LitePose forward on the sm_100a kernels.
+
+``LitePoseEngine`` turns a reference-compatible state_dict (names/shapes of
+reference lib/models/pose_mobilenet.py:21-156) into BN-folded, kernel-packed fp16
+weights (fold recipe: reference fuse_bn.py:81-137,147-162; shared-BN deconv pair:
+scale into both branches, shift once) and runs the network as a fixed sequence of
+C-ABI calls (include/litepose_b200.h) on NHWC fp16 activations.  A plan (buffers +
+call list) is built per (N, H, W, dtype) and can be captured into a CUDA graph.
+PyTorch is used for device memory and streams only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+EPS = 1e-5
+
+
+def _fold(sd, bn):
+    s = sd[bn + ".weight"].float() / torch.sqrt(sd[bn + ".running_var"].float() + EPS)
+    b = sd[bn + ".bias"].float() - sd[bn + ".running_mean"].float() * s
+    return s, b
+
+
+def _np16(t):
+    """fp32 tensor -> contiguous uint16 view of its fp16 rounding (host)."""
+    return np.ascontiguousarray(t.detach().float().cpu().half().numpy()).view(np.uint16)
+
+
+class _Op(object):
+    __slots__ = ("fn", "args", "name")
+
+    def __init__(self, name, fn, args):
+        self.name, self.fn, self.args = name, fn, args
+
+
+class LitePoseEngine(object):
+    def __init__(self, state_dict, arch, device, num_joints_out=None):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lp_device_check(), "lp_device_check")
+        self.arch = arch
+        self.plans = {}
+        self.use_graphs = False
+        sd = {k: v.detach() for k, v in state_dict.items()}
+        self._prep(sd)
+
+    # ------------------------------------------------------------------ weights
+    def _dev(self, arr, dtype):
+        return torch.from_numpy(np.ascontiguousarray(arr)).view(dtype).to(self.device)
+
+    def _pack_pw(self, w, bias):
+        n, k = w.shape[0], w.shape[1]
+        w16 = _np16(w.reshape(n, k))
+        wp = np.zeros(self.lib.lp_pw1x1_packed_elems(k, n), np.uint16)
+        bp = np.zeros(self.lib.lp_pw1x1_packed_bias_elems(n), np.float32)
+        b = None if bias is None else np.ascontiguousarray(bias.detach().float().cpu().numpy())
+        _lib.check(self.lib.lp_pw1x1_pack(w16.ctypes.data, None if b is None else b.ctypes.data, k, n,
+                                          wp.ctypes.data, bp.ctypes.data), "lp_pw1x1_pack")
+        return {"w": self._dev(wp, torch.float16), "b": self._dev(bp, torch.float32), "K": k, "N": n}
+
+    def _pack_dw(self, w, bias):
+        c, k = w.shape[0], w.shape[-1]
+        wt = w.reshape(c, k * k).t().contiguous()   # tap-major [k*k][C]
+        return {"w": wt.half().to(self.device), "b": bias.float().contiguous().to(self.device), "C": c, "k": k}
+
+    def _prep(self, sd):
+        arch = self.arch
+        P = {}
+        s, b = _fold(sd, "first.0.1")
+        w = sd["first.0.0.weight"].float() * s.view(-1, 1, 1, 1)
+        P["stem"] = {"w": w.reshape(32, 27).half().contiguous().to(self.device),
+                     "b": b.contiguous().to(self.device)}
+        s, b = _fold(sd, "first.1.1")
+        P["stem_dw"] = self._pack_dw(sd["first.1.0.weight"].float() * s.view(-1, 1, 1, 1), b)
+        s, b = _fold(sd, "first.3")
+        P["stem_pw"] = self._pack_pw(sd["first.2.weight"].float() * s.view(-1, 1, 1, 1), b)
+        self.channels = [sd["first.2.weight"].shape[0]]
+        blocks = []
+        for si, st in enumerate(arch["backbone_setting"]):
+            for bi in range(st["num_blocks"]):
+                p = "stage.%d.%d." % (si, bi)
+                stride = st["stride"] if bi == 0 else 1
+                s, b = _fold(sd, p + "inv.1")
+                inv = self._pack_pw(sd[p + "inv.0.weight"].float() * s.view(-1, 1, 1, 1), b)
+                s, b = _fold(sd, p + "depth_conv.1")
+                dw = self._pack_dw(sd[p + "depth_conv.0.weight"].float() * s.view(-1, 1, 1, 1), b)
+                s, b = _fold(sd, p + "point_conv.1")
+                pc = self._pack_pw(sd[p + "point_conv.0.weight"].float() * s.view(-1, 1, 1, 1), b)
+                cin, cout = inv["K"], pc["N"]
+                blocks.append({"inv": inv, "dw": dw, "pc": pc, "stride": stride, "stage": si,
+                               "res": stride == 1 and cin == cout, "last": bi == st["num_blocks"] - 1})
+            self.channels.append(blocks[-1]["pc"]["N"])
+        P["blocks"] = blocks
+        P["deconv"] = []
+        P["heads"] = []
+        for i in range(3):
+            s, b = _fold(sd, "deconv_bnrelu.%d.0" % i)
+            wr = sd["deconv_refined.%d.weight" % i].float() * s.view(1, -1, 1, 1)
+            ww = sd["deconv_raw.%d.weight" % i].float() * s.view(1, -1, 1, 1)
+            cr, cw, co = wr.shape[0], ww.shape[0], wr.shape[1]
+            wp = np.zeros(self.lib.lp_deconv_packed_elems(cr, cw, co), np.uint16)
+            bp = np.zeros(self.lib.lp_deconv_packed_bias_elems(co), np.float32)
+            bb = np.ascontiguousarray(b.cpu().numpy())
+            a, c = _np16(wr), _np16(ww)
+            _lib.check(self.lib.lp_deconv_pack(a.ctypes.data, c.ctypes.data, bb.ctypes.data, cr, cw, co,
+                                               wp.ctypes.data, bp.ctypes.data), "lp_deconv_pack")
+            P["deconv"].append({"w": self._dev(wp, torch.float16), "b": self._dev(bp, torch.float32),
+                                "Cr": cr, "Cw": cw, "Co": co})
+            if i > 0:
+                hd = {}
+                for nm in ("final_refined", "final_raw"):
+                    p = "%s.%d.conv." % (nm, i - 1)
+                    s, b = _fold(sd, p + "1")
+                    hd[nm + "_dw"] = self._pack_dw(sd[p + "0.weight"].float() * s.view(-1, 1, 1, 1), b)
+                w1 = sd["final_refined.%d.conv.3.weight" % (i - 1)].float()
+                w2 = sd["final_raw.%d.conv.3.weight" % (i - 1)].float()
+                co, c1, c2 = w1.shape[0], w1.shape[1], w2.shape[1]
+                wp = np.zeros(self.lib.lp_head_packed_elems(c1, c2, co), np.uint16)
+                a, c = _np16(w1.reshape(co, c1)), _np16(w2.reshape(co, c2))
+                _lib.check(self.lib.lp_head_pack(a.ctypes.data, c.ctypes.data, c1, c2, co, wp.ctypes.data),
+                           "lp_head_pack")
+                hd.update({"w": self._dev(wp, torch.float16), "C1": c1, "C2": c2, "Co": co})
+                P["heads"].append(hd)
+        self.P = P
+
+    # ------------------------------------------------------------------ plan
+    def _build_plan(self, n, h, w, in_dtype, out_fp32):
+        if h % 16 or w % 16:
+            raise ValueError("LitePose input height/width must be multiples of 16, got %dx%d" % (h, w))
+        lib, P, dev = self.lib, self.P, self.device
+        f16 = torch.float16
+        ops = []
+
+        def buf(*shape):
+            return torch.empty(shape, dtype=f16, device=dev)
+
+        plan = {"in_ptr": ctypes.c_void_p(0), "flip": ctypes.c_int(0)}
+        h2, w2 = h // 2, w // 2
+        a0 = buf(n, h2, w2, 32)
+        a1 = buf(n, h2, w2, 32)
+        x0 = buf(n, h2, w2, P["stem_pw"]["N"])
+        st = P["stem"]
+        ops.append(_Op("stem", lib.lp_stem_conv3x3_s2,
+                       [plan["in_ptr"], 1 if in_dtype == torch.float32 else 0, plan["flip"], st["w"].data_ptr(),
+                        st["b"].data_ptr(), a0.data_ptr(), n, h, w]))
+        d = P["stem_dw"]
+        ops.append(_Op("stem_dw", lib.lp_dwconv_f16, [a0.data_ptr(), d["w"].data_ptr(), d["b"].data_ptr(),
+                                                       a1.data_ptr(), n, 32, h2, w2, 3, 1, _lib.ACT_RELU6]))
+        q = P["stem_pw"]
+        ops.append(_Op("stem_pw", lib.lp_pw1x1_f16, [a1.data_ptr(), q["w"].data_ptr(), q["b"].data_ptr(), None,
+                                                      x0.data_ptr(), n * h2 * w2, q["K"], q["N"], _lib.ACT_NONE]))
+        keep = [a0, a1, x0]
+        x_list = [(x0, h2, w2)]
+        cur, ch, cw_ = x0, h2, w2
+        # scratch for the expanded tensors, sized for the largest block
+        max_e = max_d = 0
+        th, tw = h2, w2
+        for blk in P["blocks"]:
+            e = n * th * tw * blk["inv"]["N"]
+            th2, tw2 = th // blk["stride"], tw // blk["stride"]
+            max_e = max(max_e, e)
+            max_d = max(max_d, n * th2 * tw2 * blk["dw"]["C"])
+            th, tw = th2, tw2
+        e_buf = torch.empty(max_e, dtype=f16, device=dev)
+        d_buf = torch.empty(max_d, dtype=f16, device=dev)
+        keep += [e_buf, d_buf]
+        for blk in P["blocks"]:
+            inv, dw, pc = blk["inv"], blk["dw"], blk["pc"]
+            oh, ow = ch // blk["stride"], cw_ // blk["stride"]
+            ops.append(_Op("inv", lib.lp_pw1x1_f16, [cur.data_ptr(), inv["w"].data_ptr(), inv["b"].data_ptr(), None,
+                                                      e_buf.data_ptr(), n * ch * cw_, inv["K"], inv["N"],
+                                                      _lib.ACT_RELU6]))
+            ops.append(_Op("dw7", lib.lp_dwconv_f16, [e_buf.data_ptr(), dw["w"].data_ptr(), dw["b"].data_ptr(),
+                                                       d_buf.data_ptr(), n, dw["C"], ch, cw_, dw["k"], blk["stride"],
+                                                       _lib.ACT_RELU6]))
+            out = buf(n, oh, ow, pc["N"])
+            keep.append(out)
+            ops.append(_Op("pc", lib.lp_pw1x1_f16, [d_buf.data_ptr(), pc["w"].data_ptr(), pc["b"].data_ptr(),
+                                                     cur.data_ptr() if blk["res"] else None, out.data_ptr(),
+                                                     n * oh * ow, pc["K"], pc["N"], _lib.ACT_NONE]))
+            cur, ch, cw_ = out, oh, ow
+            if blk["last"]:
+                x_list.append((cur, ch, cw_))
+        refined, rh, rw = x_list[-1]
+        raw = x_list[-2][0]
+        outs = []
+        for i in range(3):
+            dc = P["deconv"][i]
+            nxt = buf(n, rh * 2, rw * 2, dc["Co"])
+            keep.append(nxt)
+            ops.append(_Op("deconv", lib.lp_fusion_deconv_f16,
+                           [refined.data_ptr(), raw.data_ptr(), dc["w"].data_ptr(), dc["b"].data_ptr(),
+                            nxt.data_ptr(), n, rh, rw, dc["Cr"], dc["Cw"], dc["Co"]]))
+            refined, rh, rw = nxt, rh * 2, rw * 2
+            raw = x_list[-i - 3][0]
+            if i > 0:
+                hd = P["heads"][i - 1]
+                t1, t2 = buf(n, rh, rw, hd["C1"]), buf(n, rh, rw, hd["C2"])
+                keep += [t1, t2]
+                for src, dst, key in ((refined, t1, "final_refined_dw"), (raw, t2, "final_raw_dw")):
+                    dd = hd[key]
+                    ops.append(_Op("head_dw", lib.lp_dwconv_f16,
+                                   [src.data_ptr(), dd["w"].data_ptr(), dd["b"].data_ptr(), dst.data_ptr(), n,
+                                    dd["C"], rh, rw, dd["k"], 1, _lib.ACT_RELU]))
+                o = torch.empty((n, hd["Co"], rh, rw), dtype=torch.float32 if out_fp32 else f16, device=dev)
+                outs.append(o)
+                ops.append(_Op("head_pw", lib.lp_head_pw_dual_f16,
+                               [t1.data_ptr(), t2.data_ptr(), hd["w"].data_ptr(), o.data_ptr(), 1 if out_fp32 else 0,
+                                n, rh, rw, hd["C1"], hd["C2"], hd["Co"]]))
+        plan.update({"ops": ops, "outs": outs, "keep": keep, "graph": None, "static_in": None})
+        return plan
+
+    def plan_for(self, n, h, w, in_dtype, out_fp32):
+        key = (n, h, w, in_dtype, out_fp32)
+        pl = self.plans.get(key)
+        if pl is None:
+            pl = self._build_plan(n, h, w, in_dtype, out_fp32)
+            self.plans[key] = pl
+        return pl
+
+    # ------------------------------------------------------------------ run
+    def _launch_all(self, plan, stream_ptr):
+        for op in plan["ops"]:
+            rc = op.fn(*op.args, stream_ptr)
+            if rc:
+                _lib.check(rc, op.name)
+
+    def run(self, x, flip=False, out_fp32=True, clone=True):
+        """x: NCHW fp16/fp32 CUDA tensor.  Returns [out0 [N,2J,H/4,W/4], out1 [N,J,H/2,W/2]]
+        (fp32 when out_fp32 else fp16).  ``flip`` computes the forward of torch.flip(x,[3])."""
+        assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.float()
+        x = x.contiguous()
+        n, _, h, w = x.shape
+        plan = self.plan_for(n, h, w, x.dtype, out_fp32)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            if self.use_graphs:
+                g = plan["graph"]
+                if g is None:
+                    g = plan["graph"] = {}
+                key = bool(flip)
+                if plan["static_in"] is None:
+                    plan["static_in"] = torch.empty_like(x)
+                plan["static_in"].copy_(x)
+                if key not in g:
+                    plan["in_ptr"].value = plan["static_in"].data_ptr()
+                    plan["flip"].value = 1 if flip else 0
+                    self._launch_all(plan, stream)      # warm-up (also sets func attributes)
+                    torch.cuda.current_stream().synchronize()
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
+                        self._launch_all(plan, torch.cuda.current_stream().cuda_stream)
+                    g[key] = cg
+                g[key].replay()
+            else:
+                plan["in_ptr"].value = x.data_ptr()
+                plan["flip"].value = 1 if flip else 0
+                self._launch_all(plan, stream)
+        outs = plan["outs"]
+        return [o.clone() for o in outs] if clone else list(outs)

@@ -176,11 +176,45 @@ def adjust(ans, det):
     return ans
 
 
+def _row_sum_f32(col):
+    """ATen CPU ``row_sum`` (aten/src/ATen/native/cpu/SumKernel.cpp): four interleaved
+    partial sums over full groups of 4, tail added to partial 0, partials folded
+    left to right; everything in float32 starting from 0."""
+    f = np.float32
+    n = len(col)
+    g = n // 4
+    p = [f(0), f(0), f(0), f(0)]
+    for i in range(g):
+        for k in range(4):
+            p[k] = f(p[k] + col[4 * i + k])
+    for i in range(4 * g, n):
+        p[0] = f(p[0] + col[i])
+    for k in range(1, 4):
+        p[0] = f(p[0] + p[k])
+    return p[0]
+
+
 def _mean_f32_rows(rows):
-    """torch.mean(dim=0) of a stacked [m,T] fp32 tensor on the CPU (group.py:220):
-    pinned empirically against torch in tests/test_oracle_vs_reference.py."""
-    import torch
-    return torch.mean(torch.from_numpy(np.stack(rows).astype(np.float32)), dim=0).numpy()
+    """``torch.mean(torch.cat(tags, 0), dim=0)`` of an [m,T] fp32 CPU tensor
+    (group.py:220) restated: ATen sums columns in groups of 4 sequentially over the
+    rows (``multi_row_sum``) and each left-over column with ``row_sum``; the mean
+    divides the fp32 sum by m.  Verified bit-exact against torch 2.11 for T in 2..6
+    and for T == 1 with m < 8 (tests/test_oracle_vs_reference.py).  For T == 1 and
+    m >= SIMD width torch switches to a vectorised inner sum whose order depends on
+    the host CPU (AVX2 vs AVX-512), i.e. the reference itself is not reproducible
+    there; the scalar ``row_sum`` order is the canonical choice of this oracle."""
+    a = np.stack(rows).astype(np.float32)
+    m, t = a.shape
+    out = np.zeros(t, np.float32)
+    full = (t // 4) * 4
+    for c in range(full):
+        s = np.float32(0)
+        for i in range(m):
+            s = np.float32(s + a[i, c])
+        out[c] = s
+    for c in range(full, t):
+        out[c] = _row_sum_f32(a[:, c])
+    return (out / np.float32(m)).astype(np.float32)
 
 
 def refine(det, tag, keypoints):
