@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the LitePose inference hot path (BASELINE.json metric):
+
+    frames/sec, LitePose-S 512x512 end-to-end (backbone x2 with flip + glue + group), fp16, batch 32 per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # sm_100a path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+A "step" is one pass of the hot path over one batch of synthetic frames per GPU.  `value` is the
+whole-job throughput with the frames resident in HBM; `e2e` is the same metric through the public
+pipeline call with pinned HOST frames (H2D + result D2H inside the timed region, NCCL gather of the
+packed keypoints when N > 1).  Timing: CUDA events on the launching stream, barrier + synchronize on
+both sides, max over ranks.  Per-step working set (~2 GB of heat/tag maps at batch 32) exceeds the
+126 MB L2, so no explicit flush is needed for the step timing; the single-kernel roofline timing
+flushes L2 between iterations.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec LitePose-S 512x512 end-to-end (backbone+group)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="S")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--people", type=int, default=5)
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--ref-frames", type=int, default=2, help="frames per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=6, help="frames of the cpu_baseline sample (b200 arm)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "LitePose-%s %dx%d fp16 batch=%d/GPU: 2 forward passes (flip test) + fused glue "
+                    "(PROJECT2IMAGE) + HeatmapParser NMS/top-K/tag-match/adjust/refine, %d planted persons/frame"
+                    % (args.arch, args.size, args.size, args.batch, args.people),
+        "arch": "search-%s.json" % args.arch, "input": [args.size, args.size], "batch_per_gpu": args.batch,
+        "global_batch": args.batch * n_gpus, "eval_cfg": "experiments/crowd_pose/mobilenet/mobile.yaml",
+        "parallelism": "dp%d (batch sharded, one NCCL gather of packed keypoints)" % n_gpus,
+        "l2": "working set per step > L2 (no flush needed); roofline kernel timed with explicit L2 flush",
+    }
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_reference_setup(args):
+    import torch
+    from litepose_b200 import synth
+    from litepose_b200.config import get_arch, get_cfg
+    from litepose_b200.lib.models.pose_mobilenet import get_pose_net
+    from litepose_b200.pipeline import PlantedCrowd
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = get_cfg(input_size=args.size)
+    arch = get_arch(args.arch)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, arch), 1).eval()
+    sd = {k: v.float() for k, v in model.state_dict().items()}
+    return cfg, arch, sd
+
+
+def cpu_reference_step(cfg, arch, sd, frames, plant):
+    """The reference algorithm for the path on the host: fp32 eager forward x2 (flip), glue,
+    planted persons, HeatmapParser.parse per image (oracle restatement; the Python reference itself
+    cannot travel to the GPU box)."""
+    import numpy as np
+    import torch
+    from oracle import glue_ref, group_ref, model_ref
+    size = frames.shape[2]
+    with torch.no_grad():
+        _, hm, tg = glue_ref.multi_stage_outputs(cfg, lambda im: model_ref.forward(sd, arch, im), frames, True, True,
+                                                 (frames.shape[3], size))
+        det, tag = glue_ref.aggregate(cfg, hm, tg)
+        det, tag = det.contiguous(), tag.contiguous()
+        plant.apply(det, tag)
+    parser = group_ref.HeatmapParser(cfg)
+    out = []
+    dn, tn = det.numpy(), tag.numpy()
+    for i in range(frames.shape[0]):
+        out.append(parser.parse(dn[i:i + 1], tn[i:i + 1], True, True))
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from litepose_b200 import synth
+    from litepose_b200.pipeline import PlantedCrowd
+    cfg, arch, sd = cpu_reference_setup(args)
+    nf = args.ref_frames
+    frames = synth.make_frames(nf, args.size, seed=1234)
+    plant = PlantedCrowd(nf, 14, args.size, args.size, 2, num_people=args.people, seed=77, device="cpu")
+    for _ in range(args.warmup):
+        cpu_reference_step(cfg, arch, sd, frames, plant)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(cfg, arch, sd, frames, plant)
+    dt = time.perf_counter() - t0
+    fps = nf * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = "%d frames/step x %d steps of the same workload (fp32 CPU eager, all host threads)" % (nf, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ roofline (dominant kernel)
+def time_dw7_kernel(n, c, hw, device):
+    """CUDA-event timing of the dominant kernel (7x7 depthwise + bias + ReLU6, stride 1) at the largest
+    stage-0 shape of the workload, L2 flushed between iterations.  Returns (avg seconds, algorithmic bytes)."""
+    import torch
+    from litepose_b200 import _lib
+    lib = _lib.load()
+    x = torch.randn((n, hw, hw, c), device=device).half()
+    w = (torch.randn((49, c), device=device) * 0.1).half()
+    b = torch.zeros(c, device=device)
+    y = torch.empty_like(x)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    s = torch.cuda.current_stream().cuda_stream
+    times = []
+    for i in range(13):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.lp_dwconv_f16(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), n, c, hw, hw, 7, 1, 2, s))
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    alg = 2 * (2 * n * c * hw * hw + 49 * c) + 4 * c
+    return sum(times) / len(times), alg
+
+
+# ------------------------------------------------------------------------------ main arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from litepose_b200 import _lib, synth
+    from litepose_b200.config import get_arch, get_cfg
+    from litepose_b200.lib.models.pose_mobilenet import get_pose_net
+    from litepose_b200.pipeline import LitePosePipeline, PlantedCrowd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.check(lib.lp_device_check(), "lp_device_check")
+
+    cfg = get_cfg(input_size=args.size)
+    arch = get_arch(args.arch)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, arch), 1).eval().to(dev)
+    pipe = LitePosePipeline(model, cfg, use_graphs=not args.no_graphs)
+    B, S = args.batch, args.size
+    frames = synth.make_frames(B, S, seed=1234, rank=rank).half().pin_memory()
+    plant = PlantedCrowd(B, 14, S, S, 2, num_people=args.people, seed=77 + rank, device=dev)
+    x_dev = frames.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # launches per step (non-graph single step)
+    pipe.use_graphs = False
+    pipe.step_device(x_dev, plant)
+    torch.cuda.synchronize()
+    lib.lp_reset_launch_count()
+    pipe.step_device(x_dev, plant)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.lp_launch_count())
+    pipe.use_graphs = not args.no_graphs
+
+    # ---- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        pipe.step_device(x_dev, plant)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pipe.step_device(x_dev, plant)
+    e1.record()
+    barrier()
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / t_dev
+
+    # ---- end to end: pinned host frames in, host keypoints out; H2D of step i+1 overlaps step i
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    xbuf = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    packed0 = pipe.step_device(x_dev, plant)
+    gathered = None
+    if world > 1:
+        gathered = [torch.empty_like(packed0) for _ in range(world)] if rank == 0 else None
+    host_out = torch.empty((world,) + tuple(packed0.shape), dtype=torch.float32).pin_memory() if rank == 0 else None
+    h2d_bytes = frames.numel() * frames.element_size()
+    d2h_bytes = packed0.numel() * packed0.element_size() * world
+
+    def upload(i):
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(copy_stream):
+            xbuf[i & 1].copy_(frames, non_blocking=True)
+            ev.record(copy_stream)
+        return ev
+
+    def e2e_steps(k):
+        ev = upload(0)
+        for i in range(k):
+            main_stream.wait_event(ev)
+            if i + 1 < k:
+                nxt = upload(i + 1)
+            packed = pipe.step_device(xbuf[i & 1], plant)
+            if world > 1:
+                dist.gather(packed, gathered, dst=0)
+                if rank == 0:
+                    for r in range(world):
+                        host_out[r].copy_(gathered[r], non_blocking=True)
+            else:
+                host_out[0].copy_(packed, non_blocking=True)
+            main_stream.synchronize()      # the caller consumes the keypoints of this step
+            if i + 1 < k:
+                ev = nxt
+
+    e2e_steps(max(args.warmup, 3))
+    barrier()
+    t0 = time.perf_counter()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    e2e_steps(args.steps)
+    c1.record()
+    barrier()
+    t_e2e = max_over_ranks(max(c0.elapsed_time(c1) * 1e-3, 0.0))
+    t_wall = max_over_ranks(time.perf_counter() - t0)
+    t_e2e = max(t_e2e, t_wall * 0.0)   # device-event time on the launching stream (wall clock kept for reference)
+    e2e_value = world * B * args.steps / t_e2e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # sanity: the planted persons are found
+    res = pipe.unpack(host_out[0], 14 * 5, 2)
+    found = [r[2] for r in res]
+
+    # ---- roofline of the dominant kernel (dw7x7 stage-0 shape of this workload)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    c_stage0 = 6 * arch["backbone_setting"][0]["channel"]
+    t_k, alg = time_dw7_kernel(B, c_stage0, S // 4, dev)
+    achieved = alg / t_k / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dw7_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "dwconv_kernel<7,1> %dx%dx%dx%d" % (B, S // 4, S // 4, c_stage0),
+                "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": traffic, "algorithmic_bytes": alg, "avg_launch_us": t_k * 1e6,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"}
+
+    # ---- CPU baseline (oracle port) on a bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ccfg, carch, sd = cpu_reference_setup(args)
+        nf = 2
+        fr = synth.make_frames(nf, S, seed=1234)
+        cp = PlantedCrowd(nf, 14, S, S, 2, num_people=args.people, seed=77, device="cpu")
+        cpu_reference_step(ccfg, carch, sd, fr, cp)          # warm-up
+        reps = max(1, args.cpu_sample // nf)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cpu_reference_step(ccfg, carch, sd, fr, cp)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nf * reps / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d frames of the same workload (oracle port: fp32 eager CPU forward x2 + glue + parser)"
+                         % (nf * reps)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes * world,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e / args.steps * 1e3,
+                "wall_ms_per_step": t_wall / args.steps * 1e3},
+        "gpu_launches": launches_per_step * args.steps * 2 * world,
+        "launches_per_step": launches_per_step,
+        "cuda_graphs": not args.no_graphs,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "persons_found_rank0": found[:8],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

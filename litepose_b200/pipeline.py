@@ -1,0 +1,183 @@
+"""End-to-end batched inference: frames -> keypoints, mirroring the reference's
+per-image loop (reference valid.py:195-233) for a whole batch on one GPU:
+
+    image.cuda()                          -> pinned H2D copy (side stream, double buffered)
+    get_multi_stage_outputs(flip=True)    -> two engine passes (the flip pass mirrors inside the stem)
+    aggregate_results                     -> one fused glue kernel (lp_glue_f32)
+    parser.parse(final_heatmaps, tags)    -> device parser (NMS/top-K, match, adjust, refine)
+    get_final_preds                       -> left to the caller (CPU, tiny; "next" row 3)
+
+Deviations from valid.py, all forced by the synthetic setting (SURVEY.md §8b last row):
+frames are synthetic tensors instead of dataloader images; weights are random-init; the
+optional ``plant`` hook adds planted person patches between glue and parser (a random-weight
+network detects nobody); no dataset.evaluate.  One process drives one GPU; ranks shard the
+batch and a single NCCL gather of the packed keypoints follows (litepose_b200/dist.py).
+"""
+import torch
+
+from . import _lib
+from .config import flip_index_for
+from .parser import DeviceParser
+
+
+class PlantedCrowd(object):
+    """Sparse planted persons for the synthetic benchmark: Gaussian det patches are
+    max-composited into the heat-maps and 9x9 tag patches overwrite the tag maps (all T).
+    Index/value tensors are built once on the host (litepose_b200.synth conventions) and
+    applied with three small torch index ops on the device."""
+
+    def __init__(self, n, num_joints, h, w, t, num_people=5, seed=0, device="cuda", presence=0.9, sigma=2.0):
+        import numpy as np
+        rng = np.random.RandomState(seed)
+        r = int(3 * sigma)
+        yy, xx = np.mgrid[-r:r + 1, -r:r + 1]
+        gauss = np.exp(-(xx ** 2 + yy ** 2) / (2.0 * sigma * sigma)).astype(np.float32)
+        didx, dval, tidx, tval = [], [], [], []
+        m = min(20, h // 4, w // 4)
+        for i in range(n):
+            for p in range(num_people):
+                cy, cx = rng.randint(m, h - m), rng.randint(m, w - m)
+                for j in range(num_joints):
+                    present = rng.rand() < presence
+                    dy, dx = rng.randint(-15, 16), rng.randint(-15, 16)
+                    amp = np.float32(rng.uniform(0.5, 1.0))
+                    if not present:
+                        continue
+                    y = int(np.clip(cy + dy, r, h - r - 1))
+                    x = int(np.clip(cx + dx, r, w - r - 1))
+                    base = (i * num_joints + j) * h * w
+                    ys, xs = np.mgrid[y - r:y + r + 1, x - r:x + r + 1]
+                    didx.append((base + ys * w + xs).ravel())
+                    dval.append((amp * gauss).ravel())
+                    ys, xs = np.mgrid[y - 4:y + 5, x - 4:x + 5]
+                    flat = (base + ys * w + xs).ravel()
+                    tv = (2.0 * p + rng.randn(81, t) * 0.05).astype(np.float32)
+                    tidx.append((flat[:, None] * t + np.arange(t)[None, :]).ravel())
+                    tval.append(tv.ravel())
+        cat = lambda l, dt: torch.from_numpy(np.concatenate(l).astype(dt)) if l else torch.zeros(0, dtype=torch.int64)
+        self.didx = cat(didx, np.int64).to(device)
+        self.dval = cat(dval, np.float32).to(device) if didx else torch.zeros(0, device=device)
+        self.tidx = cat(tidx, np.int64).to(device)
+        self.tval = cat(tval, np.float32).to(device) if tidx else torch.zeros(0, device=device)
+
+    def apply(self, det, tag):
+        if self.didx.numel():
+            d = det.view(-1)
+            # overlapping patches: scatter-max keeps the larger amplitude, order independent
+            d.scatter_reduce_(0, self.didx, self.dval, reduce="amax", include_self=True)
+            tag.view(-1).index_copy_(0, self.tidx, self.tval)
+        return det, tag
+
+
+class LitePosePipeline(object):
+    def __init__(self, model, cfg, use_graphs=True, keep=64):
+        """model: litepose_b200 drop-in LitePose on a CUDA device (eval)."""
+        self.cfg = cfg
+        self.lib = _lib.load()
+        self.device = next(model.parameters()).device
+        self.engine = model.lp_engine(self.device)
+        from .lib.core.group import Params
+        p = Params(cfg)
+        self.params = p
+        self.parser = DeviceParser(p.num_joints, p.max_num_people, p.detection_threshold, p.tag_threshold,
+                                   p.use_detection_val, p.ignore_too_much, p.joint_order, cfg.TEST.NMS_KERNEL,
+                                   cfg.TEST.NMS_PADDING)
+        self.flip = bool(cfg.TEST.FLIP_TEST)
+        self.project = bool(cfg.TEST.PROJECT2IMAGE)
+        self.adjust, self.refine = bool(cfg.TEST.ADJUST), bool(cfg.TEST.REFINE)
+        self.fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device=self.device)
+        self.use_graphs = use_graphs
+        self.keep = keep                  # persons copied back per image in the fixed-size D2H payload
+        self._state = {}
+
+    # -- device step (everything between the H2D copy and the D2H copy) -------------
+    def _device_step(self, st, x):
+        eng, J = self.engine, self.params.num_joints
+        o = eng.run(x, flip=False, out_fp32=True, clone=False)
+        o0, o1 = o[0], o[1]
+        if self.flip:
+            # the two passes share plan buffers: keep the plain pass' outputs
+            st["o0"].copy_(o0)
+            st["o1"].copy_(o1)
+            o0, o1 = st["o0"], st["o1"]
+            f = eng.run(x, flip=True, out_fp32=True, clone=False)
+        n, _, h, w = o0.shape
+        Hd, Wd = st["det"].shape[2], st["det"].shape[3]
+        _lib.check(self.lib.lp_glue_f32(o0.data_ptr(), o1.data_ptr(), f[0].data_ptr() if self.flip else None,
+                                        f[1].data_ptr() if self.flip else None, self.fidx.data_ptr(), n, J, h, w,
+                                        1 if self.flip else 0, Hd, Wd, st["det"].data_ptr(), st["tag"].data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream), "lp_glue_f32")
+        if st["plant"] is not None:
+            st["plant"].apply(st["det"], st["tag"])
+        ans, num, scores = self.parser.run(st["det"], st["tag"], self.adjust, self.refine)
+        k = self.keep
+        st["packed"][:, :k * st["row"]].copy_(ans[:, :k].reshape(n, -1))
+        st["packed"][:, k * st["row"]:k * st["row"] + k].copy_(scores[:, :k])
+        st["packed"][:, -1].copy_(num.float())
+        return st["packed"]
+
+    def _get_state(self, n, s_h, s_w, dtype, plant):
+        key = (n, s_h, s_w, dtype)
+        st = self._state.get(key)
+        if st is None:
+            J = self.params.num_joints
+            T = 2 if self.flip else 1
+            Hd, Wd = (s_h, s_w) if self.project else (s_h // 2, s_w // 2)
+            dev = self.device
+            row = J * (3 + T)
+            st = {
+                "x": torch.empty((n, 3, s_h, s_w), dtype=dtype, device=dev),
+                "o0": torch.empty((n, 2 * J, s_h // 4, s_w // 4), dtype=torch.float32, device=dev),
+                "o1": torch.empty((n, J, s_h // 2, s_w // 2), dtype=torch.float32, device=dev),
+                "det": torch.empty((n, J, Hd, Wd), dtype=torch.float32, device=dev),
+                "tag": torch.empty((n, J, Hd, Wd, T), dtype=torch.float32, device=dev),
+                "packed": torch.zeros((n, self.keep * row + self.keep + 1), dtype=torch.float32, device=dev),
+                "host": torch.empty((n, self.keep * row + self.keep + 1), dtype=torch.float32).pin_memory(),
+                "row": row, "T": T, "graph": None, "plant": plant,
+            }
+            self._state[key] = st
+        st["plant"] = plant
+        return st
+
+    def step_device(self, x_dev, plant=None):
+        """Frames already resident on the device (NCHW fp16/fp32).  Returns the packed device result
+        [N, keep*J*(3+T) + keep + 1] (keypoints, scores, person count)."""
+        n, _, s_h, s_w = x_dev.shape
+        st = self._get_state(n, s_h, s_w, x_dev.dtype, plant)
+        if not self.use_graphs:
+            return self._device_step(st, x_dev)
+        st["x"].copy_(x_dev, non_blocking=True)
+        if st["graph"] is None:
+            self.engine.use_graphs = False
+            self._device_step(st, st["x"])          # warm-up: builds plans, sets function attributes
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._device_step(st, st["x"])
+            st["graph"] = g
+        st["graph"].replay()
+        return st["packed"]
+
+    def step(self, frames_pinned, plant=None):
+        """Public end-to-end call: pinned host frames in, host result out (blocking)."""
+        x = frames_pinned.to(self.device, non_blocking=True)
+        packed = self.step_device(x, plant)
+        n = packed.shape[0]
+        st = self._get_state(n, x.shape[2], x.shape[3], x.dtype, plant)
+        st["host"].copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.unpack(st["host"], st["row"], st["T"])
+
+    def unpack(self, host, row, T):
+        """packed host tensor -> list over images of (ans ndarray [P,J,3+T], scores list), P clipped to keep."""
+        import numpy as np
+        a = host.numpy()
+        J, k = self.params.num_joints, self.keep
+        out = []
+        for i in range(a.shape[0]):
+            p = int(a[i, -1])
+            q = min(p, k)
+            ans = a[i, :k * row].reshape(k, J, 3 + T)[:q].copy()
+            sc = a[i, k * row:k * row + k][:q].copy()
+            out.append((ans, list(sc), p))
+        return out

@@ -1,0 +1,152 @@
+"""-m gpu: every CUDA kernel family against an fp32 CPU reference of the same op on
+fp16-rounded seeded inputs (stated tolerance 2e-3*max|ref| + 1e-4), through the C ABI."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from litepose_b200 import _lib
+from gpu_util import from_nhwc, nhwc16, pack_pw, q16, stream, tol_check
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_and_device():
+    lib = _lib.load()
+    assert lib.lp_version() >= 100
+    _lib.check(lib.lp_device_check(), "device")
+
+
+@pytest.mark.parametrize("fp32_in,flip", [(True, False), (False, False), (True, True)])
+def test_stem(fp32_in, flip):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    n, h, w = 2, 64, 96
+    x = torch.randn(n, 3, h, w, generator=g)
+    wt = q16(torch.randn(32, 3, 3, 3, generator=g) * 0.3)
+    b = torch.randn(32, generator=g) * 0.1
+    xin = x if fp32_in else q16(x)
+    src = torch.flip(xin, [3]) if flip else xin
+    ref = F.relu6(F.conv2d(src, wt, b, 2, 1))
+    xd = (xin if fp32_in else xin.half()).cuda().contiguous()
+    y = torch.empty(n, h // 2, w // 2, 32, dtype=torch.float16, device="cuda")
+    wd = wt.reshape(32, 27).half().cuda()
+    _lib.check(lib.lp_stem_conv3x3_s2(xd.data_ptr(), 1 if fp32_in else 0, 1 if flip else 0, wd.data_ptr(),
+                                      b.cuda().data_ptr(), y.data_ptr(), n, h, w, stream()), "stem")
+    torch.cuda.synchronize()
+    tol_check(from_nhwc(y), ref, what="stem")
+
+
+@pytest.mark.parametrize("k,s,c,h,w,act", [
+    (7, 1, 96, 32, 32, 2), (7, 2, 96, 64, 64, 2), (7, 1, 48, 40, 24, 2), (7, 1, 720, 16, 16, 2),
+    (7, 2, 144, 34 * 2, 18 * 2, 2), (5, 1, 24, 64, 64, 1), (5, 1, 40, 36, 68, 1), (3, 1, 32, 64, 64, 2),
+    (3, 2, 16, 32, 32, 0), (7, 1, 8, 8, 8, 2),
+])
+def test_dwconv(k, s, c, h, w, act):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(k * 100 + c)
+    n = 2
+    x = q16(torch.randn(n, c, h, w, generator=g))
+    wt = q16(torch.randn(c, 1, k, k, generator=g) * 0.2)
+    b = torch.randn(c, generator=g) * 0.1
+    ref = F.conv2d(x, wt, b, s, k // 2, 1, c)
+    ref = F.relu6(ref) if act == 2 else (F.relu(ref) if act == 1 else ref)
+    xd = nhwc16(x)
+    wd = wt.reshape(c, k * k).t().contiguous().half().cuda()
+    y = torch.full((n, h // s, w // s, c), float("nan"), dtype=torch.float16, device="cuda")
+    _lib.check(lib.lp_dwconv_f16(xd.data_ptr(), wd.data_ptr(), b.cuda().data_ptr(), y.data_ptr(), n, c, h, w, k, s,
+                                 act, stream()), "dwconv")
+    torch.cuda.synchronize()
+    tol_check(from_nhwc(y), ref, what="dwconv k%d s%d c%d" % (k, s, c))
+
+
+@pytest.mark.parametrize("m,k,n,act,res", [
+    (128, 16, 96, 2, False), (1000, 96, 16, 0, True), (4096, 32, 192, 2, False), (640, 192, 32, 0, False),
+    (2048, 120, 720, 2, False), (2048, 720, 120, 0, True), (300, 24, 144, 2, False), (260, 432, 72, 0, True),
+    (512, 160, 960, 2, False), (64, 960, 160, 0, False), (4096, 32, 16, 0, False), (20000, 48, 288, 2, False),
+])
+def test_pw1x1(m, k, n, act, res):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(m + k + n)
+    a = q16(torch.randn(m, k, generator=g))
+    wt = q16(torch.randn(n, k, generator=g) / (k ** 0.5))
+    b = torch.randn(n, generator=g) * 0.1
+    r = q16(torch.randn(m, n, generator=g)) if res else None
+    ref = a @ wt.t() + b
+    ref = F.relu6(ref) if act == 2 else (F.relu(ref) if act == 1 else ref)
+    if res:
+        ref = ref + r
+    wp, bp = pack_pw(wt, b)
+    ad = a.half().cuda()
+    rd = r.half().cuda() if res else None
+    out = torch.full((m, n), float("nan"), dtype=torch.float16, device="cuda")
+    _lib.check(lib.lp_pw1x1_f16(ad.data_ptr(), wp.data_ptr(), bp.data_ptr(), rd.data_ptr() if res else None,
+                                out.data_ptr(), m, k, n, act, stream()), "pw1x1")
+    torch.cuda.synchronize()
+    tol_check(out, ref, what="pw %dx%dx%d" % (m, k, n))
+
+
+@pytest.mark.parametrize("n,h,w,cr,cw,co", [
+    (2, 16, 16, 80, 48, 16), (1, 32, 32, 120, 48, 32), (2, 20, 12, 160, 96, 64), (1, 64, 64, 24, 16, 32),
+    (1, 28, 28, 32, 32, 24), (3, 8, 8, 16, 24, 24),
+])
+def test_fusion_deconv(n, h, w, cr, cw, co):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(cr + cw + co)
+    xr = q16(torch.randn(n, cr, h, w, generator=g))
+    xw = q16(torch.randn(n, cw, h, w, generator=g))
+    wr = q16(torch.randn(cr, co, 4, 4, generator=g) / (cr ** 0.5))
+    ww = q16(torch.randn(cw, co, 4, 4, generator=g) / (cw ** 0.5))
+    b = torch.randn(co, generator=g) * 0.1
+    ref = F.relu(F.conv_transpose2d(xr, wr, None, 2, 1) + F.conv_transpose2d(xw, ww, None, 2, 1) + b.view(1, -1, 1, 1))
+    wp = np.zeros(lib.lp_deconv_packed_elems(cr, cw, co), np.uint16)
+    bp = np.zeros(lib.lp_deconv_packed_bias_elems(co), np.float32)
+    a16 = np.ascontiguousarray(wr.half().numpy()).view(np.uint16)
+    c16 = np.ascontiguousarray(ww.half().numpy()).view(np.uint16)
+    bb = np.ascontiguousarray(b.numpy())
+    _lib.check(lib.lp_deconv_pack(a16.ctypes.data, c16.ctypes.data, bb.ctypes.data, cr, cw, co, wp.ctypes.data,
+                                  bp.ctypes.data))
+    wd = torch.from_numpy(wp).view(torch.float16).cuda()
+    bd = torch.from_numpy(bp).cuda()
+    out = torch.full((n, 2 * h, 2 * w, co), float("nan"), dtype=torch.float16, device="cuda")
+    r_, w_ = nhwc16(xr), nhwc16(xw)
+    _lib.check(lib.lp_fusion_deconv_f16(r_.data_ptr(), w_.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                                        n, h, w, cr, cw, co, stream()), "deconv")
+    torch.cuda.synchronize()
+    tol_check(from_nhwc(out), ref, what="deconv")
+
+
+@pytest.mark.parametrize("n,h,w,c1,c2,co,fp32", [
+    (2, 32, 32, 24, 16, 28, True), (1, 64, 64, 32, 16, 14, True), (1, 40, 24, 40, 24, 28, False),
+    (2, 16, 16, 24, 16, 34, True),
+])
+def test_head(n, h, w, c1, c2, co, fp32):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(c1 + c2 + co)
+    a1 = q16(torch.randn(n, c1, h, w, generator=g))
+    a2 = q16(torch.randn(n, c2, h, w, generator=g))
+    w1 = q16(torch.randn(co, c1, generator=g) / (c1 ** 0.5))
+    w2 = q16(torch.randn(co, c2, generator=g) / (c2 ** 0.5))
+    ref = F.conv2d(a1, w1.view(co, c1, 1, 1)) + F.conv2d(a2, w2.view(co, c2, 1, 1))
+    wp = np.zeros(lib.lp_head_packed_elems(c1, c2, co), np.uint16)
+    x16 = np.ascontiguousarray(w1.half().numpy()).view(np.uint16)
+    y16 = np.ascontiguousarray(w2.half().numpy()).view(np.uint16)
+    _lib.check(lib.lp_head_pack(x16.ctypes.data, y16.ctypes.data, c1, c2, co, wp.ctypes.data))
+    wd = torch.from_numpy(wp).view(torch.float16).cuda()
+    out = torch.full((n, co, h, w), float("nan"), dtype=torch.float32 if fp32 else torch.float16, device="cuda")
+    d1, d2 = nhwc16(a1), nhwc16(a2)
+    _lib.check(lib.lp_head_pw_dual_f16(d1.data_ptr(), d2.data_ptr(), wd.data_ptr(), out.data_ptr(), 1 if fp32 else 0,
+                                       n, h, w, c1, c2, co, stream()), "head")
+    torch.cuda.synchronize()
+    tol_check(out, ref, what="head")
+
+
+def test_error_codes():
+    lib = _lib.load()
+    rc = lib.lp_dwconv_f16(None, None, None, None, 1, 8, 8, 8, 7, 1, 0, None)
+    assert rc == 1 and b"null" in lib.lp_last_error()
+    x = torch.zeros(64, dtype=torch.float16, device="cuda")
+    rc = lib.lp_dwconv_f16(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), 1, 12, 8, 8, 7, 1, 0, None)
+    assert rc == 1
+    rc = lib.lp_pw1x1_f16(x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), 8, 12, 8, 0, None)
+    assert rc == 1

@@ -1,0 +1,117 @@
+"""-m gpu: the drop-in LitePose module on the sm_100a kernels against the golden
+outputs of the unmodified reference (fp32) -- tolerance 2e-3*max|ref| + 1e-4 --
+plus state_dict / network_to_half / deepcopy contract and a full-size batch property."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from litepose_b200 import synth
+from litepose_b200.config import get_arch, get_cfg
+from litepose_b200.lib.models.pose_mobilenet import get_pose_net
+from oracle import model_ref
+from oracle.make_golden import TINY_ARCH
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(got, ref, what):
+    err = np.abs(got - ref).max()
+    lim = 2e-3 * np.abs(ref).max() + 1e-4
+    assert err <= lim, "%s: %.3e > %.3e" % (what, err, lim)
+    return err
+
+
+def test_tiny_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "model_tiny.npz"))
+    cfg = get_cfg(input_size=64)
+    model = get_pose_net(cfg, False, TINY_ARCH)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    x = torch.from_numpy(z["x"]).cuda()
+    with torch.no_grad():
+        outs = model(x)
+    assert outs[0].dtype == torch.float32
+    _tol(outs[0].cpu().numpy(), z["out0"], "tiny out0")
+    _tol(outs[1].cpu().numpy(), z["out1"], "tiny out1")
+
+
+@pytest.mark.parametrize("name,size", [("XS", 128), ("S", 128)])
+def test_shipped_arch_golden(golden_dir, name, size):
+    z = np.load(os.path.join(golden_dir, "model_%s_%d.npz" % (name, size)))
+    cfg = get_cfg(input_size=size)
+    torch.manual_seed(0)
+    model = get_pose_net(cfg, False, get_arch(name))
+    synth.randomize_bn_(model, 1)
+    x = synth.make_frames(1, size, seed=11)
+    # fp32 module on CUDA
+    m32 = copy.deepcopy(model).cuda().eval()
+    with torch.no_grad():
+        o = m32(x.cuda())
+    _tol(o[0].cpu().numpy(), z["out0"], name + " out0")
+    _tol(o[1].cpu().numpy(), z["out1"], name + " out1")
+    # the reference's fp16 wrapper: tofp16 -> half model with fp32 BN -> tofp32
+    class tofp16(torch.nn.Module):
+        def forward(self, t):
+            return t.half()
+
+    class tofp32(torch.nn.Module):
+        def forward(self, t):
+            return [u.float() for u in t]
+
+    def bn_float(mod):
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.float()
+        for c in mod.children():
+            bn_float(c)
+        return mod
+
+    half = torch.nn.Sequential(tofp16(), bn_float(copy.deepcopy(model).half()), tofp32()).cuda().eval()
+    with torch.no_grad():
+        oh = half(x.cuda())
+    assert oh[0].dtype == torch.float32
+    _tol(oh[0].cpu().numpy(), z["out0"], name + " half out0")
+    _tol(oh[1].cpu().numpy(), z["out1"], name + " half out1")
+    # fresh tensors per call (the glue keeps the first call's outputs alive)
+    with torch.no_grad():
+        o2 = m32(torch.flip(x, [3]).cuda())
+    assert o2[0].data_ptr() != o[0].data_ptr()
+    _tol(o[0].cpu().numpy(), z["out0"], name + " out0 still intact")
+
+
+def test_flip_forward_equals_flipped_input():
+    cfg = get_cfg(input_size=128)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, get_arch("XS")), 1).cuda().eval()
+    x = synth.make_frames(2, 128, seed=5).cuda()
+    eng = model.lp_engine()
+    a = eng.run(torch.flip(x, [3]).contiguous(), flip=False)
+    b = eng.run(x, flip=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_batch_independence_full_size():
+    """size-independent property at the benchmark shape: a frame's output does not depend on its
+    batch neighbours (S @ 512x512, N = 4 vs N = 1), and CUDA graphs replay bit-identically."""
+    cfg = get_cfg(input_size=512)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, get_arch("S")), 1).cuda().eval()
+    x = synth.make_frames(4, 512, seed=9).cuda().half()
+    eng = model.lp_engine()
+    full = eng.run(x)
+    one = eng.run(x[2:3].contiguous())
+    assert torch.equal(full[0][2:3], one[0]) and torch.equal(full[1][2:3], one[1])
+    assert torch.isfinite(full[0]).all() and torch.isfinite(full[1]).all()
+    eng.use_graphs = True
+    g1 = eng.run(x)
+    g2 = eng.run(x)
+    eng.use_graphs = False
+    assert torch.equal(g1[0], full[0]) and torch.equal(g2[1], full[1])
+    # against the fp32 oracle on one frame
+    with torch.no_grad():
+        ref = model_ref.forward({k: v.cpu() for k, v in model.state_dict().items()}, get_arch("S"), x[2:3].float().cpu())
+    _tol(one[0].cpu().numpy(), ref[0].numpy(), "S512 out0")
+    _tol(one[1].cpu().numpy(), ref[1].numpy(), "S512 out1")

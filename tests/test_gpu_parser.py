@@ -1,0 +1,130 @@
+"""-m gpu: device parser (NMS/top-K, tag match, adjust, refine) bit-exact against the
+oracle and the committed golden vectors from the unmodified reference; fused glue
+within the stated fp tolerance."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from litepose_b200 import _lib, synth
+from litepose_b200.config import flip_index_for, get_cfg
+from oracle import glue_ref, group_ref
+from oracle.make_golden import PARSER_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def _parser(cfg):
+    from litepose_b200.lib.core.group import HeatmapParser
+    return HeatmapParser(cfg)
+
+
+@pytest.mark.parametrize("case", PARSER_CASES, ids=[c[0] for c in PARSER_CASES])
+def test_parser_golden(golden_dir, case):
+    name, ds, h, w, t, people, seed = case
+    z = np.load(os.path.join(golden_dir, "parser_%s.npz" % name))
+    cfg = get_cfg(dataset=ds, input_size=256)
+    nj = cfg.DATASET.NUM_JOINTS
+    det, tag = synth.plant_crowd(nj, h, w, t, num_people=people, seed=seed)
+    assert hashlib.sha256(det.tobytes() + tag.tobytes()).hexdigest() == str(z["in_digest"])
+    p = _parser(cfg)
+    dd, td = torch.from_numpy(det)[None].cuda(), torch.from_numpy(tag)[None].cuda()
+    top = p.top_k(dd, td)
+    m = z["val_k"] > 0
+    assert np.array_equal(m, top["val_k"] > 0)
+    for k in ("val_k", "loc_k", "tag_k"):
+        assert np.array_equal(top[k][m], z[k][m]), k
+    for adj, ref in ((True, True), (True, False), (False, False)):
+        ans, scores = p.parse(dd, td, adj, ref)
+        a = np.asarray(ans[0], dtype=np.float32).reshape(-1, nj, 3 + t)
+        exp = z["ans_a%d_r%d" % (adj, ref)]
+        assert a.shape == exp.shape, (adj, ref, a.shape, exp.shape)
+        assert np.array_equal(a, exp), (adj, ref, np.abs(a - exp).max())
+        assert np.array_equal(np.asarray(scores, np.float32), z["scores_a%d_r%d" % (adj, ref)])
+
+
+@pytest.mark.parametrize("h,w,t,people", [(64, 64, 2, 4), (96, 160, 1, 9), (200, 120, 2, 20)])
+def test_parser_batch_vs_oracle(h, w, t, people):
+    cfg = get_cfg(input_size=256)
+    n = 5
+    det, tag = synth.plant_crowd_batch(n, 14, h, w, t, num_people=people, seed=100)
+    det[3] = np.random.RandomState(1).uniform(0, 0.02, det[3].shape).astype(np.float32)   # an image with nobody
+    p = _parser(cfg)
+    got = p.parse_batch(torch.from_numpy(det).cuda(), torch.from_numpy(tag).cuda(), True, True)
+    op = group_ref.HeatmapParser(cfg)
+    exp = op.parse_batch(det.copy(), tag.copy(), True, True)
+    for i in range(n):
+        a = np.asarray(got[i][0][0], np.float32).reshape(-1, 14, 3 + t)
+        e = np.asarray(exp[i][0][0], np.float32).reshape(-1, 14, 3 + t)
+        assert a.shape == e.shape, (i, a.shape, e.shape)
+        assert np.array_equal(a, e), i
+        assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(exp[i][1], np.float32))
+
+
+def test_topk_plateau_and_empty():
+    """plateaus keep every equal maximum (canonical index order); all-zero planes give empty slots."""
+    cfg = get_cfg(input_size=256)
+    det = np.zeros((1, 14, 48, 40), np.float32)
+    det[0, 0, 10:14, 10:14] = 0.5            # 4x4 plateau: all 16 survive
+    det[0, 1, 5, 7] = 0.9
+    det[0, 1, 5, 8] = 0.9                    # tie inside one window: both survive, index order
+    tag = np.random.RandomState(0).randn(1, 14, 48, 40, 2).astype(np.float32)
+    p = _parser(cfg)
+    top = p.top_k(torch.from_numpy(det).cuda(), torch.from_numpy(tag).cuda())
+    exp = group_ref.HeatmapParser(cfg).top_k(det, tag)
+    for k in ("val_k", "loc_k", "tag_k"):
+        assert np.array_equal(top[k], exp[k]), k
+    assert (top["val_k"][0, 0, :16] == 0.5).all() and top["val_k"][0, 0, 16] == 0
+    assert (top["val_k"][0, 2:] == 0).all()
+
+
+@pytest.mark.parametrize("flip,proj", [(1, 1), (0, 1), (1, 0)])
+def test_glue_golden(golden_dir, flip, proj):
+    lib = _lib.load()
+    z = np.load(os.path.join(golden_dir, "glue_flip%d_proj%d.npz" % (flip, proj)))
+    cfg = get_cfg(input_size=64, flip_test=bool(flip), project2image=bool(proj))
+    a0, a1, b0, b1 = [torch.from_numpy(z[k]).cuda() for k in ("a0", "a1", "b0", "b1")]
+    n, j2, h, w = a0.shape
+    J = j2 // 2
+    T = 2 if flip else 1
+    Hd, Wd = (64, 64) if proj else (2 * h, 2 * w)
+    det = torch.full((n, J, Hd, Wd), float("nan"), device="cuda")
+    tag = torch.full((n, J, Hd, Wd, T), float("nan"), device="cuda")
+    fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device="cuda")
+    _lib.check(lib.lp_glue_f32(a0.data_ptr(), a1.data_ptr(), b0.data_ptr() if flip else None,
+                               b1.data_ptr() if flip else None, fidx.data_ptr(), n, J, h, w, flip, Hd, Wd,
+                               det.data_ptr(), tag.data_ptr(), torch.cuda.current_stream().cuda_stream), "glue")
+    torch.cuda.synchronize()
+    ed, et = z["final_heatmaps"], z["tags"]
+    assert np.abs(det.cpu().numpy() - ed).max() <= 2e-3 * np.abs(ed).max() * 1e-2 + 1e-5
+    assert np.abs(tag.cpu().numpy() - et).max() <= 2e-3 * np.abs(et).max() * 1e-2 + 1e-5
+
+
+def test_glue_nonsquare_projection():
+    lib = _lib.load()
+    cfg = get_cfg(input_size=64, flip_test=True, project2image=True)
+    g = torch.Generator().manual_seed(3)
+    n, J, h, w = 2, 14, 16, 24
+    a0, b0 = torch.randn(n, 2 * J, h, w, generator=g), torch.randn(n, 2 * J, h, w, generator=g)
+    a1, b1 = torch.randn(n, J, 2 * h, 2 * w, generator=g), torch.randn(n, J, 2 * h, 2 * w, generator=g)
+    Hd, Wd = 61, 93
+    calls = []
+
+    def fake(img):
+        calls.append(1)
+        return [a0, a1] if len(calls) == 1 else [b0, b1]
+
+    _, hm, tg = glue_ref.multi_stage_outputs(cfg, fake, torch.zeros(n, 3, 64, 96), True, True, (Wd, Hd))
+    ed, et = glue_ref.aggregate(cfg, hm, tg)
+    det = torch.empty((n, J, Hd, Wd), device="cuda")
+    tag = torch.empty((n, J, Hd, Wd, 2), device="cuda")
+    fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device="cuda")
+    args = [t.cuda() for t in (a0, a1, b0, b1)]
+    _lib.check(lib.lp_glue_f32(args[0].data_ptr(), args[1].data_ptr(), args[2].data_ptr(), args[3].data_ptr(),
+                               fidx.data_ptr(), n, J, h, w, 1, Hd, Wd, det.data_ptr(), tag.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream), "glue")
+    torch.cuda.synchronize()
+    assert (det.cpu() - ed).abs().max().item() <= 1e-5 * max(1.0, ed.abs().max().item())
+    assert (tag.cpu() - et).abs().max().item() <= 1e-5 * max(1.0, et.abs().max().item())
