@@ -120,7 +120,7 @@ def cpu_reference_setup(args):
     cfg = get_cfg(input_size=args.size)
     arch = get_arch(args.arch)
     torch.manual_seed(0)
-    model = synth.randomize_bn_(get_pose_net(cfg, False, arch), 1).eval()
+    model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, arch), 1)).eval()
     sd = {k: v.float() for k, v in model.state_dict().items()}
     return cfg, arch, sd
 
@@ -232,7 +232,7 @@ def main():
     cfg = get_cfg(input_size=args.size)
     arch = get_arch(args.arch)
     torch.manual_seed(0)
-    model = synth.randomize_bn_(get_pose_net(cfg, False, arch), 1).eval().to(dev)
+    model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, arch), 1)).eval().to(dev)
     pipe = LitePosePipeline(model, cfg, use_graphs=not args.no_graphs)
     B, S = args.batch, args.size
     frames = synth.make_frames(B, S, seed=1234, rank=rank).half().pin_memory()

@@ -28,6 +28,16 @@ def randomize_bn_(model, seed=1):
     return model
 
 
+def scale_heads_(model, factor=0.05):
+    """Scale the bias-free output 1x1 convs so that a random-weight network's heat-maps stay
+    below DETECTION_THRESHOLD (|heat| ~ 0.02): the planted persons are then the only detections."""
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.startswith(("final_refined", "final_raw")) and name.endswith("conv.3.weight"):
+                p.mul_(factor)
+    return model
+
+
 def make_frames(n, size, seed=1234, rank=0, width=None):
     """``torch.rand(N,3,S,S)`` then ImageNet normalisation (valid.py:181-184)."""
     g = torch.Generator().manual_seed(seed + rank)

@@ -228,15 +228,14 @@ def refine(det, tag, keypoints):
             x, y = keypoints[i][:2].astype(np.int32)
             tags.append(tag[i, y, x])
     prev_tag = _mean_f32_rows(tags)
-    d = tag - prev_tag[None, None, None, :]
-    sq = (d * d).astype(np.float32)
-    s = sq[..., 0]
-    for c in range(1, sq.shape[3]):
-        s = (s + sq[..., c]).astype(np.float32)
-    tt = np.sqrt(s).astype(np.float32)
+    # dense pass with the same fp32 torch CPU ops the reference issues (group.py:221-224); torch is
+    # multi-threaded, which keeps the CPU baseline representative of the reference's own cost
+    import torch
+    tt_ = torch.from_numpy(np.ascontiguousarray(tag))
+    dt_ = torch.from_numpy(np.ascontiguousarray(det))
+    tt = (((tt_ - torch.from_numpy(prev_tag)[None, None, None, :]) ** 2).sum(dim=3) ** 0.5)
     p, h, w = tt.shape
-    tmp2 = (det - np.round(tt)).astype(np.float32).reshape(p, -1)
-    pos = tmp2.argmax(axis=1)
+    pos = (dt_ - torch.round(tt)).view(p, -1).argmax(dim=1).numpy()
     ans = []
     for i in range(keypoints.shape[0]):
         tmp = det[i]
