@@ -1,0 +1,122 @@
+"""CPU: C-ABI surface (every symbol the header declares is exported and bound), config
+mirrors, drop-in module contract (state_dict keys, deepcopy, half wrapper on CPU), shard
+logic, and the world_size-2 gloo gather."""
+import copy
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from litepose_b200 import _lib, synth
+from litepose_b200.config import FLIP_CONFIG, get_arch, get_cfg
+from litepose_b200.dist import shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "litepose_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _lib.load()          # raises AttributeError if the .so lacks a bound symbol
+    for name in declared:
+        assert hasattr(lib, name), "header declares %s but the library does not export it" % name
+        assert name in _lib.SIGNATURES, "ctypes binding missing for %s" % name
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.lp_version() >= 100
+
+
+def test_host_side_packers_and_errors():
+    lib = _lib.load()
+    assert lib.lp_pw1x1_packed_elems(16, 96) == 96 * 64
+    assert lib.lp_pw1x1_packed_elems(120, 720) == 3 * 2 * 240 * 64
+    assert lib.lp_pw1x1_packed_bias_elems(720) == 720
+    k, n = 24, 40
+    w = (np.arange(n * k, dtype=np.float32).reshape(n, k) / 100).astype(np.float16).view(np.uint16)
+    wp = np.zeros(lib.lp_pw1x1_packed_elems(k, n), np.uint16)
+    bp = np.zeros(lib.lp_pw1x1_packed_bias_elems(n), np.float32)
+    assert lib.lp_pw1x1_pack(w.ctypes.data, None, k, n, wp.ctypes.data, bp.ctypes.data) == 0
+    t = wp.reshape(1, 1, 48, 64)
+    assert np.array_equal(t[0, 0, :n, :k], w) and not t[0, 0, n:, :].any() and not t[0, 0, :, k:].any()
+    assert lib.lp_pw1x1_pack(None, None, k, n, wp.ctypes.data, bp.ctypes.data) == 1
+    assert b"lp_pw1x1_pack" in lib.lp_last_error()
+    # deconv program: 9 shifts per 64-channel block, 16 (phase, tap) weight tiles per block
+    assert lib.lp_deconv_packed_elems(120, 48, 32) == (2 + 1) * 16 * 32 * 64
+    assert lib.lp_nms_topk_workspace_bytes(2, 14, 512, 512, 30) == 2 * 14 * 32 * 30 * 8
+
+
+def test_config_mirrors_reference_values():
+    cfg = get_cfg()
+    assert cfg.DATASET.NUM_JOINTS == 14 and cfg.TEST.NMS_KERNEL == 5 and cfg.TEST.DETECTION_THRESHOLD == 0.1
+    assert sorted(FLIP_CONFIG["CROWDPOSE"]) == list(range(14))
+    assert get_arch("S")["deconv_setting"] == [32, 24, 32]
+
+
+def test_dropin_module_contract():
+    from litepose_b200.lib.models.pose_mobilenet import get_pose_net
+    cfg = get_cfg(input_size=64)
+    model = get_pose_net(cfg, True, get_arch("XS"))
+    sd = model.state_dict()
+    assert len(sd) == 679
+    for k in ("first.0.0.weight", "stage.2.4.depth_conv.0.weight", "deconv_refined.0.weight",
+              "deconv_bnrelu.0.0.running_mean", "final_raw.1.conv.3.weight"):
+        assert k in sd
+    assert model.channel == [16, 16, 32, 48, 80] and model.num_deconv_layers == 3
+    m2 = copy.deepcopy(model)
+    m2.load_state_dict(sd, strict=True)
+    model.eval()
+    x = synth.make_frames(1, 64, seed=1)
+    with torch.no_grad():
+        o = model(x)                  # CPU tensor: module graph (the valid.py:147-150 summary call)
+    assert [tuple(t.shape) for t in o] == [(1, 28, 16, 16), (1, 14, 32, 32)]
+    half = torch.nn.Sequential(m2.half())
+    assert next(half.parameters()).dtype == torch.float16
+
+
+def test_shard_range():
+    assert [shard_range(256, r, 8) for r in range(8)] == [(32 * r, 32 * r + 32) for r in range(8)]
+    parts = [shard_range(10, r, 4) for r in range(4)]
+    assert parts == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from litepose_b200.dist import gather_packed, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(5, rank, world)
+    packed = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1).repeat(1, 7) + 0.5
+    out = gather_packed(packed, dst=0)
+    if rank == 0:
+        q.put(torch.cat(out, 0).numpy())
+    else:
+        assert out is None
+    dist.destroy_process_group()
+
+
+def test_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res.shape == (5, 7) and np.array_equal(res[:, 0], np.arange(5) + 0.5)
