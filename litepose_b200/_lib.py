@@ -36,6 +36,8 @@ SIGNATURES = {
     "lp_reset_launch_count": (None, []),
     "lp_stem_conv3x3_s2": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lp_dwconv_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lp_set_dw_precision": (None, [_i]),
+    "lp_get_dw_precision": (_i, []),
     "lp_pw1x1_packed_elems": (_sz, [_i, _i]),
     "lp_pw1x1_packed_bias_elems": (_sz, [_i]),
     "lp_pw1x1_pack": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

@@ -9,6 +9,8 @@
 // compute loop has no boundary branches.  Each thread owns one channel PAIR (half2) and walks
 // 4x4 output micro-blocks with the k*k half2 weights held in registers, accumulating in fp32.
 // Algorithmic bytes per launch: 2*(N*C*Hin*Win + N*C*Hout*Wout + C*k*k) (+4*C bias).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lp {
@@ -28,7 +30,24 @@ struct DwCfg {
     static constexpr int SMEM = IH * IW * DW_CB * 2 + 128 + 64;
 };
 
-template <int K, int S>
+// mixed-precision FMA / add (PTX ISA 8.6, sm_100+): fp16 x fp16 + fp32 -> fp32 in ONE instruction (SASS FHFMA /
+// FHADD with .H0/.H1 operand selectors), so packed half2 registers feed fp32 accumulators without conversions.
+__device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fhadd(unsigned short a, float c) {
+    float d;
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(a), "f"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned short lo16(__half2 v) { return __half_as_ushort(__low2half(v)); }
+__device__ __forceinline__ unsigned short hi16(__half2 v) { return __half_as_ushort(__high2half(v)); }
+
+// PREC 0: every product accumulated in fp32 (FHFMA).  PREC 1: the K taps of one kernel row are accumulated with
+// packed HFMA2 in fp16 (2 channels per instruction), each row sum is then added into the fp32 accumulator (FHADD).
+template <int K, int S, int PREC>
 __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict__ w, const float* __restrict__ bias,
               __half* __restrict__ y, int C, int Hout, int Wout, int tiles_x, int act) {
@@ -49,16 +68,23 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
         tma_load_4d(smem, &map_x, bar, c0, ox0 * S - K / 2, oy0 * S - K / 2, n);
     }
 
-    const int cp = threadIdx.x & 15;       // channel pair inside the slab
-    const int slot = threadIdx.x >> 4;     // 16 micro-block slots
+    const int cp = threadIdx.x & 15;           // channel pair inside the slab
+    const int sub = (threadIdx.x >> 4) & 1;    // half-warp: second half works on the x-adjacent micro-block ...
+    const int wid = threadIdx.x >> 5;
+    // ... in MIRRORED column order (stride 1), so the two half-warps always touch pixels of opposite parity
+    // (64 B per pixel = 16 banks): conflict-free LDS.  Mirrored data needs mirrored weights and mirrored stores.
+    const bool mir = (S == 1) && sub;
     const int ch = c0 + 2 * cp;
     const bool ch_ok = ch < C;
 
-    // weights for this channel pair: tap-major [k*k][C]
-    __half2 wreg[K * K];
+    __half2 wreg[K * K];   // tap-major weights [k*k][C] -> this thread's channel pair
 #pragma unroll
-    for (int t = 0; t < K * K; ++t)
-        wreg[t] = ch_ok ? *reinterpret_cast<const __half2*>(w + (size_t)t * C + ch) : __floats2half2_rn(0.f, 0.f);
+    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const int t = ky * K + (mir ? K - 1 - kx : kx);
+            wreg[ky * K + kx] = ch_ok ? *reinterpret_cast<const __half2*>(w + (size_t)t * C + ch) : __floats2half2_rn(0.f, 0.f);
+        }
     float2 b2 = make_float2(0.f, 0.f);
     if (ch_ok && bias) b2 = make_float2(bias[ch], bias[ch + 1]);
 
@@ -66,12 +92,13 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
     mbar_wait(bar, 0);
 
     const __half2* tile_in = reinterpret_cast<const __half2*>(smem);   // [IH][IW][16 pairs]
-    constexpr int BLOCKS_X = Cfg::TW / BX;
-    constexpr int NBLOCKS = (Cfg::TH / BY) * BLOCKS_X;
+    constexpr int PAIRS_X = Cfg::TW / (2 * BX);
+    constexpr int NPAIRS = (Cfg::TH / BY) * PAIRS_X;
+    const int cstep = mir ? -(DW_CB / 2) : (DW_CB / 2);
 
 #pragma unroll 1
-    for (int blk = slot; blk < NBLOCKS; blk += 16) {
-        const int by = blk / BLOCKS_X, bx = blk % BLOCKS_X;
+    for (int q = wid; q < NPAIRS; q += DW_THREADS / 32) {
+        const int by = q / PAIRS_X, bx = (q % PAIRS_X) * 2 + sub;
         const int oy = by * BY, ox = bx * BX;           // tile-local output origin
         if (oy0 + oy >= Hout || ox0 + ox >= Wout) continue;   // micro-block fully outside
         float2 acc[BY][BX];
@@ -80,23 +107,35 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
 #pragma unroll
             for (int j = 0; j < BX; ++j) acc[i][j] = b2;
 
-        const __half2* base = tile_in + ((oy * S) * Cfg::IW + ox * S) * (DW_CB / 2) + cp;
+        // slot c of a row holds input column (ox*S + c), or (ox*S + IC-1-c) when mirrored
+        const __half2* base = tile_in + ((oy * S) * Cfg::IW + ox * S + (mir ? Cfg::IC - 1 : 0)) * (DW_CB / 2) + cp;
 #pragma unroll
         for (int r = 0; r < Cfg::IR; ++r) {
-            float2 in[Cfg::IC];
+            __half2 in[Cfg::IC];
 #pragma unroll
-            for (int c = 0; c < Cfg::IC; ++c) in[c] = __half22float2(base[(r * Cfg::IW + c) * (DW_CB / 2)]);
+            for (int c = 0; c < Cfg::IC; ++c) in[c] = base[r * Cfg::IW * (DW_CB / 2) + c * cstep];
 #pragma unroll
             for (int i = 0; i < BY; ++i) {
                 const int ky = r - i * S;
                 if (ky >= 0 && ky < K) {
+                    if (PREC == 0) {
 #pragma unroll
-                    for (int kx = 0; kx < K; ++kx) {
-                        const float2 wf = __half22float2(wreg[ky * K + kx]);
+                        for (int kx = 0; kx < K; ++kx) {
+                            const __half2 wv = wreg[ky * K + kx];
+#pragma unroll
+                            for (int j = 0; j < BX; ++j) {
+                                acc[i][j].x = fhfma(lo16(in[j * S + kx]), lo16(wv), acc[i][j].x);
+                                acc[i][j].y = fhfma(hi16(in[j * S + kx]), hi16(wv), acc[i][j].y);
+                            }
+                        }
+                    } else {
 #pragma unroll
                         for (int j = 0; j < BX; ++j) {
-                            acc[i][j].x = fmaf(in[j * S + kx].x, wf.x, acc[i][j].x);
-                            acc[i][j].y = fmaf(in[j * S + kx].y, wf.y, acc[i][j].y);
+                            __half2 sacc = __hmul2(in[j * S], wreg[ky * K]);
+#pragma unroll
+                            for (int kx = 1; kx < K; ++kx) sacc = __hfma2(in[j * S + kx], wreg[ky * K + kx], sacc);
+                            acc[i][j].x = fhadd(lo16(sacc), acc[i][j].x);
+                            acc[i][j].y = fhadd(hi16(sacc), acc[i][j].y);
                         }
                     }
                 }
@@ -109,7 +148,7 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
                 if (gy >= Hout) continue;
 #pragma unroll
                 for (int j = 0; j < BX; ++j) {
-                    const int gx = ox0 + ox + j;
+                    const int gx = ox0 + ox + (mir ? BX - 1 - j : j);
                     if (gx >= Wout) continue;
                     const float vx = act_apply(acc[i][j].x, act), vy = act_apply(acc[i][j].y, act);
                     *reinterpret_cast<__half2*>(y + (((size_t)n * Hout + gy) * Wout + gx) * C + ch) =
@@ -120,7 +159,16 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
     }
 }
 
-template <int K, int S>
+static int g_dw_prec = -1;   // -1: read LP_DW_PREC once (default 0 = fp32 accumulation)
+static int dw_prec() {
+    if (g_dw_prec < 0) {
+        const char* e = getenv("LP_DW_PREC");
+        g_dw_prec = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_dw_prec;
+}
+
+template <int K, int S, int PREC>
 static int launch_dw(const void* x, const void* w, const float* bias, void* y, int N, int C, int H, int W, int act,
                      cudaStream_t stream) {
     using Cfg = DwCfg<K, S>;
@@ -131,14 +179,14 @@ static int launch_dw(const void* x, const void* w, const float* bias, void* y, i
     uint32_t box[4] = {(uint32_t)DW_CB, (uint32_t)Cfg::IW, (uint32_t)Cfg::IH, 1u};
     int rc = make_tmap(&map, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute((const void*)dwconv_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute((const void*)dwconv_kernel<K, S, PREC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dwconv)");
     const int tiles_x = (Wout + Cfg::TW - 1) / Cfg::TW, tiles_y = (Hout + Cfg::TH - 1) / Cfg::TH;
     dim3 grid(tiles_x * tiles_y, (C + DW_CB - 1) / DW_CB, N);
-    dwconv_kernel<K, S><<<grid, DW_THREADS, Cfg::SMEM, stream>>>(map, reinterpret_cast<const __half*>(w), bias,
-                                                                 reinterpret_cast<__half*>(y), C, Hout, Wout, tiles_x,
-                                                                 act);
+    dwconv_kernel<K, S, PREC><<<grid, DW_THREADS, Cfg::SMEM, stream>>>(map, reinterpret_cast<const __half*>(w), bias,
+                                                                       reinterpret_cast<__half*>(y), C, Hout, Wout,
+                                                                       tiles_x, act);
     LP_LAUNCH_CHECK("dwconv_kernel");
     return LP_OK;
 }
@@ -146,6 +194,9 @@ static int launch_dw(const void* x, const void* w, const float* bias, void* y, i
 }  // namespace lp
 
 using namespace lp;
+
+extern "C" void lp_set_dw_precision(int prec) { lp::g_dw_prec = prec ? 1 : 0; }
+extern "C" int lp_get_dw_precision(void) { return lp::dw_prec(); }
 
 extern "C" int lp_dwconv_f16(const void* x, const void* w, const float* bias, void* y, int N, int C, int H, int W, int k,
                              int stride, int act, lp_stream_t stream) {
@@ -161,10 +212,12 @@ extern "C" int lp_dwconv_f16(const void* x, const void* w, const float* bias, vo
         return LP_ERR_ALIGN;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    if (k == 7 && stride == 1) return launch_dw<7, 1>(x, w, bias, y, N, C, H, W, act, s);
-    if (k == 7 && stride == 2) return launch_dw<7, 2>(x, w, bias, y, N, C, H, W, act, s);
-    if (k == 5 && stride == 1) return launch_dw<5, 1>(x, w, bias, y, N, C, H, W, act, s);
-    if (k == 5 && stride == 2) return launch_dw<5, 2>(x, w, bias, y, N, C, H, W, act, s);
-    if (k == 3 && stride == 1) return launch_dw<3, 1>(x, w, bias, y, N, C, H, W, act, s);
-    return launch_dw<3, 2>(x, w, bias, y, N, C, H, W, act, s);
+    const int prec = dw_prec();
+#define LP_DW(KK, SS)                                                                      \
+    if (k == KK && stride == SS)                                                           \
+        return prec ? launch_dw<KK, SS, 1>(x, w, bias, y, N, C, H, W, act, s)              \
+                    : launch_dw<KK, SS, 0>(x, w, bias, y, N, C, H, W, act, s);
+    LP_DW(7, 1) LP_DW(7, 2) LP_DW(5, 1) LP_DW(5, 2) LP_DW(3, 1) LP_DW(3, 2)
+#undef LP_DW
+    return LP_ERR_BAD_ARG;
 }

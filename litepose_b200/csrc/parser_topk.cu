@@ -31,6 +31,8 @@ static inline int strip_rows(int W) {
     return sr;
 }
 
+constexpr int TK_LIST = 2048;   // compacted survivor list per strip (overflow -> dense scan fallback)
+
 // partial: [N*J][strips][K] keys
 __global__ void __launch_bounds__(TK_THREADS)
 nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*window radius*/, int SR, int K,
@@ -40,51 +42,80 @@ nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*windo
     const int strip = blockIdx.x, nstrips = gridDim.x;
     const int y0 = strip * SR;
     const int rows = min(SR, H - y0);
-    const int hrows = rows + 2 * R;                // rows incl. halo (clamped rows hold -inf)
+    const int hrows = rows + 2 * R;                // rows incl. halo (out-of-image rows hold -inf)
     float* s_val = sm;                             // [SR+2R][W] raw values
     float* s_hmax = sm + (size_t)(SR + 2 * R) * W; // [SR+2R][W] horizontal window max
+    __shared__ unsigned long long s_list[TK_LIST];
     __shared__ unsigned long long s_red[TK_THREADS / 32];
     __shared__ unsigned long long s_win;
+    __shared__ int s_count;
     const float* p = det + (size_t)plane * H * W;
     const float NEG_INF = __int_as_float(0xff800000);
+    if (threadIdx.x == 0) s_count = 0;
 
-    for (int i = threadIdx.x; i < hrows * W; i += TK_THREADS) {
-        const int r = i / W, x = i - r * W;
+    // rows are walked with x = tid + m*256 so no integer division is needed
+    for (int r = 0; r < hrows; ++r) {
         const int gy = y0 - R + r;
-        s_val[i] = (gy >= 0 && gy < H) ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
+        const bool in = gy >= 0 && gy < H;
+        for (int x = threadIdx.x; x < W; x += TK_THREADS) s_val[r * W + x] = in ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < hrows * W; i += TK_THREADS) {
-        const int r = i / W, x = i - r * W;
-        float m = NEG_INF;
-        const int xa = max(x - R, 0), xb = min(x + R, W - 1);
-        for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[r * W + xx]);
-        s_hmax[i] = m;
-    }
+    for (int r = 0; r < hrows; ++r)
+        for (int x = threadIdx.x; x < W; x += TK_THREADS) {
+            float m = NEG_INF;
+            const int xa = max(x - R, 0), xb = min(x + R, W - 1);
+            for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[r * W + xx]);
+            s_hmax[r * W + x] = m;
+        }
     __syncthreads();
-    // NMS'd value into s_val's centre rows (in place is safe: each thread touches only its own pixel of s_val
-    // and reads s_hmax)
-    for (int i = threadIdx.x; i < rows * W; i += TK_THREADS) {
-        const int r = i / W, x = i - r * W;
-        float m = NEG_INF;
-        for (int d = 0; d <= 2 * R; ++d) m = fmaxf(m, s_hmax[(r + d) * W + x]);
-        const float v = s_val[(r + R) * W + x];
-        s_val[(r + R) * W + x] = (v == m && v > 0.f) ? v : 0.f;
-    }
+    // NMS survivors (v == window max, v > 0): compact their keys; also keep the NMS'd value in place for the
+    // dense fallback (each thread touches only its own pixel of s_val and reads s_hmax)
+    for (int r = 0; r < rows; ++r)
+        for (int x = threadIdx.x; x < W; x += TK_THREADS) {
+            float m = NEG_INF;
+            for (int d = 0; d <= 2 * R; ++d) m = fmaxf(m, s_hmax[(r + d) * W + x]);
+            const float v = s_val[(r + R) * W + x];
+            const bool keep = (v == m && v > 0.f);
+            s_val[(r + R) * W + x] = keep ? v : 0.f;
+            if (keep) {
+                const int slot = atomicAdd(&s_count, 1);
+                if (slot < TK_LIST) {
+                    const unsigned idx = (unsigned)((y0 + r) * W + x);
+                    s_list[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
+                }
+            }
+        }
     __syncthreads();
+    const int count = s_count;
+    const bool dense = count > TK_LIST;
+    // compact path: every thread keeps its share of the list in registers
+    constexpr int PER = TK_LIST / TK_THREADS;
+    unsigned long long mine[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int q = threadIdx.x + i * TK_THREADS;
+        mine[i] = (!dense && q < count) ? s_list[q] : 0ull;
+    }
 
     unsigned long long prev = ~0ull;
     unsigned long long* out = partial + ((size_t)plane * nstrips + strip) * K;
     for (int k = 0; k < K; ++k) {
         unsigned long long best = 0ull;
-        for (int i = threadIdx.x; i < rows * W; i += TK_THREADS) {
-            const int r = i / W, x = i - r * W;
-            const float v = s_val[(r + R) * W + x];
-            if (v > 0.f) {
-                const unsigned idx = (unsigned)((y0 + r) * W + x);
-                const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
-                if (key < prev && key > best) best = key;
-            }
+        if (!dense) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i)
+                if (mine[i] < prev && mine[i] > best) best = mine[i];
+        } else {
+            for (int r = 0; r < rows; ++r)
+                for (int x = threadIdx.x; x < W; x += TK_THREADS) {
+                    const float v = s_val[(r + R) * W + x];
+                    if (v > 0.f) {
+                        const unsigned idx = (unsigned)((y0 + r) * W + x);
+                        const unsigned long long key =
+                            ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
+                        if (key < prev && key > best) best = key;
+                    }
+                }
         }
         best = shfl_max_u64(best);
         if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;

@@ -29,8 +29,22 @@ def tol_check(got, ref, rel=2e-3, abs_=1e-4, what=""):
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     err = (got - ref).abs().max().item()
     lim = rel * ref.abs().max().item() + abs_
+    _record(what, err, lim)
     assert err <= lim, "%s: max err %.3e > %.3e (max|ref| %.3e)" % (what, err, lim, ref.abs().max().item())
     return err
+
+
+def _record(what, err, lim):
+    """Append measured error / limit to gpurun_out/errors.jsonl (headroom bookkeeping, best effort)."""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "errors.jsonl"), "a") as f:
+            f.write(json.dumps({"what": what, "err": err, "lim": lim, "ratio": err / lim if lim else None}) + "\n")
+    except OSError:
+        pass
 
 
 def pack_pw(w, bias):

@@ -42,8 +42,10 @@ def test_stem(fp32_in, flip):
     (7, 2, 144, 34 * 2, 18 * 2, 2), (5, 1, 24, 64, 64, 1), (5, 1, 40, 36, 68, 1), (3, 1, 32, 64, 64, 2),
     (3, 2, 16, 32, 32, 0), (7, 1, 8, 8, 8, 2),
 ])
-def test_dwconv(k, s, c, h, w, act):
+@pytest.mark.parametrize("prec", [0, 1])
+def test_dwconv(k, s, c, h, w, act, prec):
     lib = _lib.load()
+    lib.lp_set_dw_precision(prec)
     g = torch.Generator().manual_seed(k * 100 + c)
     n = 2
     x = q16(torch.randn(n, c, h, w, generator=g))
@@ -57,7 +59,8 @@ def test_dwconv(k, s, c, h, w, act):
     _lib.check(lib.lp_dwconv_f16(xd.data_ptr(), wd.data_ptr(), b.cuda().data_ptr(), y.data_ptr(), n, c, h, w, k, s,
                                  act, stream()), "dwconv")
     torch.cuda.synchronize()
-    tol_check(from_nhwc(y), ref, what="dwconv k%d s%d c%d" % (k, s, c))
+    lib.lp_set_dw_precision(0)
+    tol_check(from_nhwc(y), ref, what="dwconv k%d s%d c%d prec%d" % (k, s, c, prec))
 
 
 @pytest.mark.parametrize("m,k,n,act,res", [

@@ -18,8 +18,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _tol(got, ref, what):
-    err = np.abs(got - ref).max()
-    lim = 2e-3 * np.abs(ref).max() + 1e-4
+    from gpu_util import _record
+    err = float(np.abs(got - ref).max())
+    lim = float(2e-3 * np.abs(ref).max() + 1e-4)
+    _record(what, err, lim)
     assert err <= lim, "%s: %.3e > %.3e" % (what, err, lim)
     return err
 
@@ -115,3 +117,23 @@ def test_batch_independence_full_size():
         ref = model_ref.forward({k: v.cpu() for k, v in model.state_dict().items()}, get_arch("S"), x[2:3].float().cpu())
     _tol(one[0].cpu().numpy(), ref[0].numpy(), "S512 out0")
     _tol(one[1].cpu().numpy(), ref[1].numpy(), "S512 out1")
+
+
+@pytest.mark.parametrize("name,size", [("XS", 128), ("S", 128)])
+def test_shipped_arch_golden_fp16_rowsum_depthwise(golden_dir, name, size):
+    """the packed-fp16 row-sum depthwise mode (lp_set_dw_precision(1)) must stay inside the same tolerance"""
+    from litepose_b200 import _lib
+    lib = _lib.load()
+    z = np.load(os.path.join(golden_dir, "model_%s_%d.npz" % (name, size)))
+    cfg = get_cfg(input_size=size)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, get_arch(name)), 1).cuda().eval()
+    x = synth.make_frames(1, size, seed=11).cuda()
+    lib.lp_set_dw_precision(1)
+    try:
+        with torch.no_grad():
+            o = model(x)
+    finally:
+        lib.lp_set_dw_precision(0)
+    _tol(o[0].cpu().numpy(), z["out0"], name + " prec1 out0")
+    _tol(o[1].cpu().numpy(), z["out1"], name + " prec1 out1")

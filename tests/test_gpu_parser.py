@@ -128,3 +128,20 @@ def test_glue_nonsquare_projection():
     torch.cuda.synchronize()
     assert (det.cpu() - ed).abs().max().item() <= 1e-5 * max(1.0, ed.abs().max().item())
     assert (tag.cpu() - et).abs().max().item() <= 1e-5 * max(1.0, et.abs().max().item())
+
+
+def test_topk_dense_fallback():
+    """more than 2048 NMS survivors in one strip (large plateau) takes the dense-scan path"""
+    cfg = get_cfg(input_size=256)
+    rng = np.random.RandomState(4)
+    det = rng.uniform(0, 0.02, (1, 14, 64, 160)).astype(np.float32)
+    det[0, 0] = 0.3                               # whole plane is one plateau: every pixel survives
+    det[0, 1, :40, :] = 0.25
+    det[0, 1, 7, 9] = 0.9
+    tag = rng.randn(1, 14, 64, 160, 1).astype(np.float32)
+    p = _parser(cfg)
+    top = p.top_k(torch.from_numpy(det).cuda(), torch.from_numpy(tag).cuda())
+    exp = group_ref.HeatmapParser(cfg).top_k(det, tag)
+    for k in ("val_k", "loc_k", "tag_k"):
+        assert np.array_equal(top[k], exp[k]), k
+    assert np.array_equal(top["loc_k"][0, 0, :, 0], np.arange(30)) and (top["loc_k"][0, 0, :, 1] == 0).all()
