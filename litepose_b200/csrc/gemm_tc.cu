@@ -23,7 +23,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;    // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;   // 32 KiB
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
+constexpr int OUT_SUB = 128 * 64 * 2;   // one 128-row x 64-column fp16 output sub-tile (128B-swizzled), 16 KiB
+constexpr int OUT_BYTES = 4 * OUT_SUB;  // staging for up to 256 output columns
 constexpr int MAX_STEPS = 48;
 constexpr int GEMM_THREADS = 192;
 constexpr int MAX_BIAS = 1024;
@@ -62,20 +64,23 @@ struct __align__(8) GemmBarriers {
     uint64_t empty[STAGES];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
+    uint64_t res_full;
     uint32_t tmem_base;
     uint32_t pad;
 };
 
-constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + MAX_BIAS * 4 + 256;
+constexpr size_t GEMM_SMEM = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + OUT_BYTES + MAX_BIAS * 4 + 256;
 
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+               const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    float* sBias = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES));
+    uint8_t* sOut = smem + STAGES * (A_BYTES + B_BYTES);   // MODE_PW: swizzled output / residual staging
+    float* sBias = reinterpret_cast<float*>(sOut + OUT_BYTES);
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sBias + MAX_BIAS);
 
     const int warp = threadIdx.x >> 5;
@@ -85,6 +90,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapA0);
         if (MODE != MODE_PW) tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
+        if (MODE == MODE_PW) {
+            tma_prefetch_desc(&mapOut);
+            if (p.residual) tma_prefetch_desc(&mapRes);
+        }
+        mbar_init(&bars->res_full, 1);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->empty[i], 1);
@@ -189,14 +199,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
             uint32_t r[16];
             if (MODE == MODE_PW) {
-                const long long m = (long long)mt * BM + row;
-                const bool valid = m < p.M;
-                __half* out = reinterpret_cast<__half*>(p.out);
+                // Output tile goes through a 128B-swizzled shared-memory staging buffer (conflict-free 16-byte
+                // st.shared) and leaves with TMA tensor stores (full 128-byte lines, rows/columns beyond M/N
+                // clipped by the tensor map); the residual tile arrives the same way.
+                const bool issuer = (threadIdx.x == 64);
+                const int ncols = min(p.n_tile, p.N - chunk * p.n_tile);       // valid columns of this chunk
+                const int nsub = (ncols + 63) >> 6;
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (p.residual) {
+                    if (issuer) {
+                        mbar_expect_tx(&bars->res_full, nsub * OUT_SUB);
+                        for (int g = 0; g < nsub; ++g)
+                            tma_load_2d(sOut + g * OUT_SUB, &mapRes, &bars->res_full, chunk * p.n_tile + g * 64, mt * BM);
+                    }
+                    mbar_wait(&bars->res_full, it & 1);
+                }
+                uint8_t* srow = sOut + row * 128;
                 for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
                     tc_ld16(taddr + c0, r);
                     tc_wait_ld();
-                    const int n0 = chunk * p.n_tile + c0;
-                    if (valid && n0 < p.N) {
+                    if (c0 < ncols) {
+                        const int n0 = chunk * p.n_tile + c0;
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBias[n0 + i];
@@ -204,26 +228,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act);
                         }
-                        const bool two = (n0 + 8) < p.N;
+                        uint8_t* sub = srow + (c0 >> 6) * OUT_SUB;
+                        const int j0 = (c0 & 63) >> 3;                        // 16-byte chunk index inside the row
+                        uint4* d0 = reinterpret_cast<uint4*>(sub + (((j0) ^ (row & 7)) << 4));
+                        uint4* d1 = reinterpret_cast<uint4*>(sub + (((j0 + 1) ^ (row & 7)) << 4));
                         if (p.residual) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.N + n0);
-                            uint4 ra = __ldg(rp);
+                            const uint4 ra = *d0, rb = *d1;
                             const __half2* h = reinterpret_cast<const __half2*>(&ra);
+                            const __half2* g = reinterpret_cast<const __half2*>(&rb);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                float2 f = __half22float2(h[i]);
+                                const float2 f = __half22float2(h[i]), e = __half22float2(g[i]);
                                 v[2 * i] += f.x;
                                 v[2 * i + 1] += f.y;
-                            }
-                            if (two) {
-                                uint4 rb = __ldg(rp + 1);
-                                const __half2* g = reinterpret_cast<const __half2*>(&rb);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    float2 f = __half22float2(g[i]);
-                                    v[8 + 2 * i] += f.x;
-                                    v[8 + 2 * i + 1] += f.y;
-                                }
+                                v[8 + 2 * i] += e.x;
+                                v[8 + 2 * i + 1] += e.y;
                             }
                         }
                         uint4 o0, o1;
@@ -234,11 +253,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             ph0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
                             ph1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
                         }
-                        uint4* op = reinterpret_cast<uint4*>(out + m * p.N + n0);
-                        op[0] = o0;
-                        if (two) op[1] = o1;
+                        *d0 = o0;
+                        *d1 = o1;
                     }
                 }
+                // accumulator drained: hand the TMEM buffer back before the store is issued
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (issuer) {
+                    for (int g = 0; g < nsub; ++g) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&mapOut)),
+                                     "r"(smem_u32(sOut + g * OUT_SUB)), "r"(chunk * p.n_tile + g * 64), "r"(mt * BM)
+                                     : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
             } else {
                 const int tx = mt % p.tiles_x;
                 const int ty = (mt / p.tiles_x) % p.tiles_y;
@@ -301,6 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
         }
+        if (MODE == MODE_PW && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -314,11 +349,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // ------------------------------------------------------------------ host side
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// N <= 256: one chunk of round_up(N,16) MMA columns.  Wider layers are cut into chunks of 192 or 256 columns (a
+// multiple of the 64-column TMA store sub-tile, so stores of neighbouring chunks never overlap), whichever pads less.
 static void pw_tiling(int N, int* n_chunks, int* n_tile) {
     const int np = round_up(N, 16);
-    const int nc = (np + 255) / 256;
-    *n_chunks = nc;
-    *n_tile = round_up((np + nc - 1) / nc, 16);
+    if (np <= 256) {
+        *n_chunks = 1;
+        *n_tile = np;
+        return;
+    }
+    const int c192 = (np + 191) / 192, c256 = (np + 255) / 256;
+    if (c192 * 192 < c256 * 256) { *n_chunks = c192; *n_tile = 192; }
+    else { *n_chunks = c256; *n_tile = 256; }
 }
 
 static int set_smem_attr_once(const void* fn) {
@@ -355,13 +397,13 @@ static void pick_spatial_tile(int H, int W, int* TH, int* TW) {
 }
 
 template <int MODE>
-static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& mo,
+                       const CUtensorMap& mr, const GemmParams& p, cudaStream_t stream) {
     int rc = set_smem_attr_once((const void*)gemm_tc_kernel<MODE>);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     if (grid < 1) return LP_OK;
-    gemm_tc_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(a0, a1, b, p);
+    gemm_tc_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(a0, a1, b, mo, mr, p);
     LP_LAUNCH_CHECK("gemm_tc_kernel");
     return LP_OK;
 }
@@ -445,7 +487,20 @@ extern "C" int lp_pw1x1_f16(const void* a, const void* w_packed, const float* bi
         rc = make_b_map(&mb, w_packed, p.n_chunks * kb * p.n_tile, p.n_tile);
         if (rc) return rc;
     }
-    return launch_gemm<MODE_PW>(ma, ma, mb, p, (cudaStream_t)stream);
+    CUtensorMap mo, mr;
+    {
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+        uint64_t strides[1] = {(uint64_t)N * 2};
+        uint32_t box[2] = {64u, (uint32_t)BM};
+        int rc = make_tmap(&mo, out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        mr = mo;
+        if (residual) {
+            rc = make_tmap(&mr, residual, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+        }
+    }
+    return launch_gemm<MODE_PW>(ma, ma, mb, mo, mr, p, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ fusion deconv
@@ -549,7 +604,7 @@ extern "C" int lp_fusion_deconv_f16(const void* refined, const void* raw, const 
     if (rc) return rc;
     rc = make_b_map(&mb, w_packed, p.total_bt * p.n_tile, p.n_tile);
     if (rc) return rc;
-    return launch_gemm<MODE_DECONV>(m0, m1, mb, p, (cudaStream_t)stream);
+    return launch_gemm<MODE_DECONV>(m0, m1, mb, mb, mb, p, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ heads
@@ -616,5 +671,5 @@ extern "C" int lp_head_pw_dual_f16(const void* a1, const void* a2, const void* w
     if (rc) return rc;
     rc = make_b_map(&mb, w_packed, p.total_bt * p.n_tile, p.n_tile);
     if (rc) return rc;
-    return launch_gemm<MODE_HEAD>(m0, m1, mb, p, (cudaStream_t)stream);
+    return launch_gemm<MODE_HEAD>(m0, m1, mb, mb, mb, p, (cudaStream_t)stream);
 }

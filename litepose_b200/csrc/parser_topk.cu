@@ -31,107 +31,113 @@ static inline int strip_rows(int W) {
     return sr;
 }
 
-constexpr int TK_LIST = 2048;   // compacted survivor list per strip (overflow -> dense scan fallback)
+constexpr int TK_SPB = 4;        // strips walked sequentially by one CTA (a "band")
+constexpr int TK_MAXW = 1024;    // candidates are collected per row: never more than W
 
-// partial: [N*J][strips][K] keys
+// Sorted insert of `key` into the descending list s_top[0..ntop) (capacity K <= 64) by one warp.
+__device__ __forceinline__ int topk_insert(unsigned long long* s_top, int ntop, int K, unsigned long long key, int lane) {
+    const unsigned long long a = lane < ntop ? s_top[lane] : 0ull;
+    const unsigned long long b = (lane + 32) < ntop ? s_top[lane + 32] : 0ull;
+    const int pos = __popc(__ballot_sync(0xffffffffu, a > key)) + __popc(__ballot_sync(0xffffffffu, b > key));
+    if (pos >= K) return ntop;
+    const int nnew = ntop < K ? ntop + 1 : K;
+    // shift [pos, nnew-1) right by one: element i takes old element i-1
+    const unsigned long long pa = __shfl_up_sync(0xffffffffu, a, 1);
+    unsigned long long pb = __shfl_up_sync(0xffffffffu, b, 1);
+    const unsigned long long a31 = __shfl_sync(0xffffffffu, a, 31);
+    if (lane == 0) pb = a31;
+    __syncwarp();
+    if (lane > pos && lane < nnew) s_top[lane] = pa;
+    if (lane + 32 > pos && lane + 32 < nnew) s_top[lane + 32] = pb;
+    if (lane == 0) s_top[pos] = key;
+    __syncwarp();
+    return nnew;
+}
+
+// partial: [N*J][bands][K] keys (sorted, 0 = empty).  One CTA walks TK_SPB strips of SR rows of one plane and
+// keeps a running top-K; only NMS survivors above the current K-th key are ever inserted, so after the first few
+// rows the selection cost vanishes and the kernel streams at memory speed.
 __global__ void __launch_bounds__(TK_THREADS)
 nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*window radius*/, int SR, int K,
                       unsigned long long* __restrict__ partial) {
     extern __shared__ __align__(16) float sm[];
     const int plane = blockIdx.y;
-    const int strip = blockIdx.x, nstrips = gridDim.x;
-    const int y0 = strip * SR;
-    const int rows = min(SR, H - y0);
-    const int hrows = rows + 2 * R;                // rows incl. halo (out-of-image rows hold -inf)
+    const int band = blockIdx.x, nbands = gridDim.x;
     float* s_val = sm;                             // [SR+2R][W] raw values
     float* s_hmax = sm + (size_t)(SR + 2 * R) * W; // [SR+2R][W] horizontal window max
-    __shared__ unsigned long long s_list[TK_LIST];
-    __shared__ unsigned long long s_red[TK_THREADS / 32];
-    __shared__ unsigned long long s_win;
-    __shared__ int s_count;
+    __shared__ unsigned long long s_top[TK_MAXK];
+    __shared__ unsigned long long s_cand[TK_MAXW];
+    __shared__ int s_ncand[2], s_ntop;   // candidate counter double-buffered by row parity (see barrier note)
     const float* p = det + (size_t)plane * H * W;
     const float NEG_INF = __int_as_float(0xff800000);
-    if (threadIdx.x == 0) s_count = 0;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { s_ncand[0] = 0; s_ncand[1] = 0; s_ntop = 0; }
+    int rowpar = 0;
+    if (threadIdx.x < TK_MAXK) s_top[threadIdx.x] = 0ull;
 
-    // rows are walked with x = tid + m*256 so no integer division is needed
-    for (int r = 0; r < hrows; ++r) {
-        const int gy = y0 - R + r;
-        const bool in = gy >= 0 && gy < H;
-        for (int x = threadIdx.x; x < W; x += TK_THREADS) s_val[r * W + x] = in ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
-    }
-    __syncthreads();
-    for (int r = 0; r < hrows; ++r)
-        for (int x = threadIdx.x; x < W; x += TK_THREADS) {
-            float m = NEG_INF;
-            const int xa = max(x - R, 0), xb = min(x + R, W - 1);
-            for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[r * W + xx]);
-            s_hmax[r * W + x] = m;
+    for (int st = 0; st < TK_SPB; ++st) {
+        const int y0 = (band * TK_SPB + st) * SR;
+        if (y0 >= H) break;
+        const int rows = min(SR, H - y0);
+        const int hrows = rows + 2 * R;            // rows incl. halo (out-of-image rows hold -inf)
+        __syncthreads();                           // previous strip fully consumed
+        for (int r = 0; r < hrows; ++r) {
+            const int gy = y0 - R + r;
+            const bool in = gy >= 0 && gy < H;
+            for (int x = threadIdx.x; x < W; x += TK_THREADS)
+                s_val[r * W + x] = in ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
         }
-    __syncthreads();
-    // NMS survivors (v == window max, v > 0): compact their keys; also keep the NMS'd value in place for the
-    // dense fallback (each thread touches only its own pixel of s_val and reads s_hmax)
-    for (int r = 0; r < rows; ++r)
-        for (int x = threadIdx.x; x < W; x += TK_THREADS) {
-            float m = NEG_INF;
-            for (int d = 0; d <= 2 * R; ++d) m = fmaxf(m, s_hmax[(r + d) * W + x]);
-            const float v = s_val[(r + R) * W + x];
-            const bool keep = (v == m && v > 0.f);
-            s_val[(r + R) * W + x] = keep ? v : 0.f;
-            if (keep) {
-                const int slot = atomicAdd(&s_count, 1);
-                if (slot < TK_LIST) {
-                    const unsigned idx = (unsigned)((y0 + r) * W + x);
-                    s_list[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
-                }
+        __syncthreads();
+        for (int r = 0; r < hrows; ++r)
+            for (int x = threadIdx.x; x < W; x += TK_THREADS) {
+                float m = NEG_INF;
+                const int xa = max(x - R, 0), xb = min(x + R, W - 1);
+                for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[r * W + xx]);
+                s_hmax[r * W + x] = m;
             }
-        }
-    __syncthreads();
-    const int count = s_count;
-    const bool dense = count > TK_LIST;
-    // compact path: every thread keeps its share of the list in registers
-    constexpr int PER = TK_LIST / TK_THREADS;
-    unsigned long long mine[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int q = threadIdx.x + i * TK_THREADS;
-        mine[i] = (!dense && q < count) ? s_list[q] : 0ull;
-    }
-
-    unsigned long long prev = ~0ull;
-    unsigned long long* out = partial + ((size_t)plane * nstrips + strip) * K;
-    for (int k = 0; k < K; ++k) {
-        unsigned long long best = 0ull;
-        if (!dense) {
-#pragma unroll
-            for (int i = 0; i < PER; ++i)
-                if (mine[i] < prev && mine[i] > best) best = mine[i];
-        } else {
-            for (int r = 0; r < rows; ++r)
-                for (int x = threadIdx.x; x < W; x += TK_THREADS) {
+        __syncthreads();
+        for (int r = 0; r < rows; ++r, rowpar ^= 1) {
+            // threshold = current K-th key (0 while the list is not full)
+            const int ntop0 = s_ntop;
+            const unsigned long long thr = ntop0 >= K ? s_top[K - 1] : 0ull;
+            for (int x0 = 0; x0 < W; x0 += TK_THREADS) {
+                const int x = x0 + threadIdx.x;
+                unsigned long long key = 0ull;
+                if (x < W) {
+                    float m = NEG_INF;
+                    for (int d = 0; d <= 2 * R; ++d) m = fmaxf(m, s_hmax[(r + d) * W + x]);
                     const float v = s_val[(r + R) * W + x];
-                    if (v > 0.f) {
+                    if (v == m && v > 0.f) {
                         const unsigned idx = (unsigned)((y0 + r) * W + x);
-                        const unsigned long long key =
-                            ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
-                        if (key < prev && key > best) best = key;
+                        key = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
                     }
                 }
-        }
-        best = shfl_max_u64(best);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            unsigned long long v = threadIdx.x < TK_THREADS / 32 ? s_red[threadIdx.x] : 0ull;
-            v = shfl_max_u64(v);
-            if (threadIdx.x == 0) { s_win = v; out[k] = v; }
-        }
-        __syncthreads();
-        prev = s_win;
-        if (prev == 0ull) {   // exhausted: remaining slots are empty
-            for (int kk = k + 1 + threadIdx.x; kk < K; kk += TK_THREADS) out[kk] = 0ull;
-            break;
+                const bool cand = key > thr;
+                const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_ncand[rowpar], __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cand) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
+                }
+            }
+            __syncthreads();
+            // block-uniform: this row's counter is not touched again before the next row's barrier (the next row
+            // counts into the other slot), so every thread reads the same value here
+            if (s_ncand[rowpar]) {
+                if (threadIdx.x < 32) {
+                    const int nc = s_ncand[rowpar];
+                    int ntop = s_ntop;
+                    for (int c = 0; c < nc; ++c) ntop = topk_insert(s_top, ntop, K, s_cand[c], lane);
+                    if (lane == 0) { s_ntop = ntop; s_ncand[rowpar] = 0; }
+                }
+                __syncthreads();
+            }
         }
     }
+    __syncthreads();
+    unsigned long long* out = partial + ((size_t)plane * nbands + band) * K;
+    for (int k = threadIdx.x; k < K; k += TK_THREADS) out[k] = k < s_ntop ? s_top[k] : 0ull;
 }
 
 // one warp per plane
@@ -185,7 +191,7 @@ using namespace lp;
 extern "C" size_t lp_nms_topk_workspace_bytes(int N, int J, int H, int W, int K) {
     if (N <= 0 || J <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     const int sr = strip_rows(W);
-    const int nstrips = (H + sr - 1) / sr;
+    const int nstrips = ((H + sr - 1) / sr + TK_SPB - 1) / TK_SPB;   // bands of TK_SPB strips
     return (size_t)N * J * nstrips * K * sizeof(unsigned long long);
 }
 
@@ -201,8 +207,8 @@ extern "C" int lp_nms_topk_f32(const float* det, const float* tag, int N, int J,
     LP_CHECK_ARG((long long)N * J <= 65535, "lp_nms_topk_f32: N*J=%lld exceeds the grid limit 65535", (long long)N * J);
     const int R = nms_kernel / 2;
     const int sr = strip_rows(W);
-    const int nstrips = (H + sr - 1) / sr;
-    LP_CHECK_ARG(nstrips <= 256, "lp_nms_topk_f32: too many strips (%d)", nstrips);
+    const int nstrips = ((H + sr - 1) / sr + TK_SPB - 1) / TK_SPB;   // bands of TK_SPB strips
+    LP_CHECK_ARG(nstrips <= 256 && W <= TK_MAXW, "lp_nms_topk_f32: plane too large (H=%d W=%d)", H, W);
     const size_t need = lp_nms_topk_workspace_bytes(N, J, H, W, K);
     if (workspace_bytes < need) {
         set_error("lp_nms_topk_f32: workspace %zu < required %zu bytes", workspace_bytes, need);

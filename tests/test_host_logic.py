@@ -34,8 +34,9 @@ def test_c_abi_exports_match_header():
 def test_host_side_packers_and_errors():
     lib = _lib.load()
     assert lib.lp_pw1x1_packed_elems(16, 96) == 96 * 64
-    assert lib.lp_pw1x1_packed_elems(120, 720) == 3 * 2 * 240 * 64
-    assert lib.lp_pw1x1_packed_bias_elems(720) == 720
+    assert lib.lp_pw1x1_packed_elems(120, 720) == 3 * 2 * 256 * 64     # 720 -> 3 chunks of 256 MMA columns
+    assert lib.lp_pw1x1_packed_bias_elems(720) == 768
+    assert lib.lp_pw1x1_packed_elems(48, 288) == 2 * 1 * 192 * 64      # 288 -> 2 chunks of 192
     k, n = 24, 40
     w = (np.arange(n * k, dtype=np.float32).reshape(n, k) / 100).astype(np.float16).view(np.uint16)
     wp = np.zeros(lib.lp_pw1x1_packed_elems(k, n), np.uint16)
@@ -47,7 +48,7 @@ def test_host_side_packers_and_errors():
     assert b"lp_pw1x1_pack" in lib.lp_last_error()
     # deconv program: 9 shifts per 64-channel block, 16 (phase, tap) weight tiles per block
     assert lib.lp_deconv_packed_elems(120, 48, 32) == (2 + 1) * 16 * 32 * 64
-    assert lib.lp_nms_topk_workspace_bytes(2, 14, 512, 512, 30) == 2 * 14 * 32 * 30 * 8
+    assert lib.lp_nms_topk_workspace_bytes(2, 14, 512, 512, 30) == 2 * 14 * 8 * 30 * 8   # 32 strips in bands of 4
 
 
 def test_config_mirrors_reference_values():
