@@ -142,17 +142,19 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
             }
         }
         if (ch_ok) {
+            const int gy0 = oy0 + oy, gx0 = ox0 + ox;
+            // one 64-bit base per micro-block; every pixel is base + (i*Wout + jj)*C elements
+            __half* ybase = y + (((size_t)n * Hout + gy0) * Wout + gx0) * C + ch;
+            const bool full = (gy0 + BY <= Hout) && (gx0 + BX <= Wout);
 #pragma unroll
             for (int i = 0; i < BY; ++i) {
-                const int gy = oy0 + oy + i;
-                if (gy >= Hout) continue;
 #pragma unroll
                 for (int j = 0; j < BX; ++j) {
-                    const int gx = ox0 + ox + (mir ? BX - 1 - j : j);
-                    if (gx >= Wout) continue;
-                    const float vx = act_apply(acc[i][j].x, act), vy = act_apply(acc[i][j].y, act);
-                    *reinterpret_cast<__half2*>(y + (((size_t)n * Hout + gy) * Wout + gx) * C + ch) =
-                        __floats2half2_rn(vx, vy);
+                    const int jj = mir ? BX - 1 - j : j;
+                    if (full || (gy0 + i < Hout && gx0 + jj < Wout)) {
+                        const float vx = act_apply(acc[i][j].x, act), vy = act_apply(acc[i][j].y, act);
+                        *reinterpret_cast<__half2*>(ybase + ((size_t)i * Wout + jj) * C) = __floats2half2_rn(vx, vy);
+                    }
                 }
             }
         }

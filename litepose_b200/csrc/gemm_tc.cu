@@ -27,7 +27,8 @@ constexpr int STAGES = 3;
 constexpr int OUT_SUB = 128 * 64 * 2;   // one 128-row x 64-column fp16 output sub-tile (128B-swizzled), 16 KiB
 constexpr int OUT_BYTES = 4 * OUT_SUB;  // staging for up to 256 output columns
 constexpr int MAX_STEPS = 48;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int EPI_THREADS = 256;
 constexpr int MAX_BIAS = 1024;
 
 enum { MODE_PW = 0, MODE_DECONV = 1, MODE_HEAD = 2 };
@@ -101,7 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->tmem_full[i], 1);
-            mbar_init(&bars->tmem_empty[i], 4);
+            mbar_init(&bars->tmem_empty[i], EPI_THREADS / 32);
         }
         fence_barrier_init();
     }
@@ -187,17 +188,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     } else {
         // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
-        const int q = warp & 3;
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;          // the two warps of a quarter take alternate 16-column groups
         const int row = q * 32 + lane;
         int it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int buf = it & 1;
             const int chunk = t % p.n_chunks;
             const int mt = t / p.n_chunks;
-            mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
             uint32_t r[16];
+            if (MODE != MODE_PW) {
+                mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+                tc_fence_after();
+            }
             if (MODE == MODE_PW) {
                 // Output tile goes through a 128B-swizzled shared-memory staging buffer (conflict-free 16-byte
                 // st.shared) and leaves with TMA tensor stores (full 128-byte lines, rows/columns beyond M/N
@@ -206,24 +210,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int ncols = min(p.n_tile, p.N - chunk * p.n_tile);       // valid columns of this chunk
                 const int nsub = (ncols + 63) >> 6;
                 if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (p.residual) {
-                    if (issuer) {
-                        mbar_expect_tx(&bars->res_full, nsub * OUT_SUB);
-                        for (int g = 0; g < nsub; ++g)
-                            tma_load_2d(sOut + g * OUT_SUB, &mapRes, &bars->res_full, chunk * p.n_tile + g * 64, mt * BM);
-                    }
-                    mbar_wait(&bars->res_full, it & 1);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (p.residual && issuer) {   // residual tile is fetched while this tile's MMAs are still running
+                    mbar_expect_tx(&bars->res_full, nsub * OUT_SUB);
+                    for (int g = 0; g < nsub; ++g)
+                        tma_load_2d(sOut + g * OUT_SUB, &mapRes, &bars->res_full, chunk * p.n_tile + g * 64, mt * BM);
                 }
+                mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+                tc_fence_after();
+                if (p.residual) mbar_wait(&bars->res_full, it & 1);
                 uint8_t* srow = sOut + row * 128;
-                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
                     tc_ld16(taddr + c0, r);
                     tc_wait_ld();
                     if (c0 < ncols) {
                         const int n0 = chunk * p.n_tile + c0;
                         float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBias[n0 + i];
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 bv = *reinterpret_cast<const float4*>(sBias + n0 + 4 * i);
+                            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bv.x;
+                            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv.y;
+                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv.z;
+                            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv.w;
+                        }
                         if (p.act != LP_ACT_NONE) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act);
@@ -262,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
                 fence_proxy_async();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (issuer) {
                     for (int g = 0; g < nsub; ++g) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -286,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int ph = 0; ph < 4; ++ph) {
                         const int a = ph >> 1, b = ph & 1;
                         __half* op = out + ((((long long)n * 2 * p.H + 2 * y + a) * (2 * p.W)) + 2 * x + b) * Co;
-                        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                        for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
                             tc_ld16(taddr + ph * p.n_tile + c0, r);
                             tc_wait_ld();
                             if (valid && c0 < Co) {
@@ -314,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const long long off = (long long)n * Co * plane + (long long)y * p.W + x;
                     float* op32 = reinterpret_cast<float*>(p.out) + off;
                     __half* op16 = reinterpret_cast<__half*>(p.out) + off;
-                    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                    for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
                         tc_ld16(taddr + c0, r);
                         tc_wait_ld();
                         if (valid) {

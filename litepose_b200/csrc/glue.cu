@@ -94,6 +94,43 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
     float* dplane = det + ((size_t)n * J + j) * Hd * Wd;
     float* tplane = tag + ((size_t)n * J + j) * Hd * Wd * T;
     const int th = oy1 - oy0 + 1, tw = ox1 - ox0 + 1;
+
+    if (project && Hd == 2 * H2 && Wd == 2 * W2 && flip) {
+        // exact x2 projection (the evaluation config): out[2m] = .25 s[m-1] + .75 s[m], out[2m+1] = .75 s[m] + .25 s[m+1]
+        // (edge-clamped).  One thread produces a 2x2 output quad from a 3x3 mid-level neighbourhood: 9 LDS per map
+        // instead of 16, constant weights, 16-byte tag stores.
+        const int qw = tw >> 1, qh = th >> 1;       // Hd, Wd and the tile origin are even
+        for (int i = threadIdx.x; i < qh * qw; i += GL_THREADS) {
+            const int qy = i / qw, qx = i - qy * qw;
+            const int m = (oy0 >> 1) + qy, k = (ox0 >> 1) + qx;              // mid-level pixel of this quad
+            const int r0 = max(m - 1, 0) - my0, r1 = m - my0, r2 = min(m + 1, H2 - 1) - my0;
+            const int c0 = max(k - 1, 0) - mx0, c1 = k - mx0, c2 = min(k + 1, W2 - 1) - mx0;
+            float o[4][4];   // [map][quad pixel: (0,0) (0,1) (1,0) (1,1)]
+#define GL_Q(S, idx)                                                                                     \
+    {                                                                                                    \
+        const float a0 = S[r0][c0], a1 = S[r0][c1], a2 = S[r0][c2];                                      \
+        const float b0 = S[r1][c0], b1 = S[r1][c1], b2 = S[r1][c2];                                      \
+        const float d0 = S[r2][c0], d1 = S[r2][c1], d2 = S[r2][c2];                                      \
+        const float al = 0.25f * a0 + 0.75f * a1, ar = 0.75f * a1 + 0.25f * a2;                          \
+        const float bl = 0.25f * b0 + 0.75f * b1, br = 0.75f * b1 + 0.25f * b2;                          \
+        const float dl = 0.25f * d0 + 0.75f * d1, dr = 0.75f * d1 + 0.25f * d2;                          \
+        o[idx][0] = 0.25f * al + 0.75f * bl;                                                             \
+        o[idx][1] = 0.25f * ar + 0.75f * br;                                                             \
+        o[idx][2] = 0.75f * bl + 0.25f * dl;                                                             \
+        o[idx][3] = 0.75f * br + 0.25f * dr;                                                             \
+    }
+            GL_Q(s_ha, 0) GL_Q(s_hf, 1) GL_Q(s_t0, 2) GL_Q(s_t1, 3)
+#undef GL_Q
+            const int Y = oy0 + 2 * qy, X = ox0 + 2 * qx;
+            const size_t o0i = (size_t)Y * Wd + X, o1i = o0i + Wd;
+            *reinterpret_cast<float2*>(dplane + o0i) = make_float2((o[0][0] + o[1][0]) / 2.f, (o[0][1] + o[1][1]) / 2.f);
+            *reinterpret_cast<float2*>(dplane + o1i) = make_float2((o[0][2] + o[1][2]) / 2.f, (o[0][3] + o[1][3]) / 2.f);
+            *reinterpret_cast<float4*>(tplane + o0i * 2) = make_float4(o[2][0], o[3][0], o[2][1], o[3][1]);
+            *reinterpret_cast<float4*>(tplane + o1i * 2) = make_float4(o[2][2], o[3][2], o[2][3], o[3][3]);
+        }
+        return;
+    }
+
     for (int i = threadIdx.x; i < th * tw; i += GL_THREADS) {
         const int ly = i / tw, lx = i - ly * tw;
         const int Y = oy0 + ly, X = ox0 + lx;
@@ -148,8 +185,8 @@ extern "C" int lp_glue_f32(const float* o0, const float* o1, const float* f0, co
         LP_CHECK_ARG((double)(2 * h) / Hd * GL_TO + 3 <= GL_TM && (double)(2 * w) / Wd * GL_TO + 3 <= GL_TM,
                      "lp_glue_f32: projection must up-sample by >= 1.73x (got %dx%d -> %dx%d)", 2 * h, 2 * w, Hd, Wd);
     }
-    if ((reinterpret_cast<uintptr_t>(tag) & 7) && flip) {
-        set_error("lp_glue_f32: tag must be 8-byte aligned");
+    if (((reinterpret_cast<uintptr_t>(tag) & 15) || (reinterpret_cast<uintptr_t>(det) & 7)) && flip) {
+        set_error("lp_glue_f32: tag must be 16-byte and det 8-byte aligned");
         return LP_ERR_ALIGN;
     }
     const int tiles_x = (Wd + GL_TO - 1) / GL_TO, tiles_y = (Hd + GL_TO - 1) / GL_TO;

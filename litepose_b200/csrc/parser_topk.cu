@@ -81,11 +81,19 @@ nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*windo
         const int rows = min(SR, H - y0);
         const int hrows = rows + 2 * R;            // rows incl. halo (out-of-image rows hold -inf)
         __syncthreads();                           // previous strip fully consumed
-        for (int r = 0; r < hrows; ++r) {
-            const int gy = y0 - R + r;
-            const bool in = gy >= 0 && gy < H;
-            for (int x = threadIdx.x; x < W; x += TK_THREADS)
-                s_val[r * W + x] = in ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
+        // batched loads: 8 independent global loads in flight per thread before the first shared store
+        for (int x = threadIdx.x; x < W; x += TK_THREADS) {
+            for (int r0 = 0; r0 < hrows; r0 += 8) {
+                float tmp[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int gy = y0 - R + r0 + u;
+                    tmp[u] = (r0 + u < hrows && gy >= 0 && gy < H) ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (r0 + u < hrows) s_val[(r0 + u) * W + x] = tmp[u];
+            }
         }
         __syncthreads();
         for (int r = 0; r < hrows; ++r)

@@ -3,24 +3,25 @@
 // later kernels.  Reference: convbnrelu(3, 32, ker=3, stride=2), lib/models/pose_mobilenet.py:37,
 // lib/models/layers/layers.py:18-24.
 //
-// CTA = 32 x 8 output pixels; the 3-channel haloed input patch is staged in shared memory as
-// fp32.  Each thread computes one output pixel x 32 channels; weights are read as warp-uniform
-// float4 broadcasts from shared memory.  Output: 64 B contiguous per thread (4 x 16-byte stores).
+// CTA = 64 x 8 output pixels; the 3-channel haloed input patch is staged in shared memory as
+// fp32 (batched global loads).  Each thread computes two x-adjacent output pixels x 32 channels;
+// weights are read as warp-uniform float4 broadcasts from shared memory (1 LDS.128 per 8 FFMA).
+// Output: 64 B contiguous per pixel (4 x 16-byte stores).
 #include "common.cuh"
 
 namespace lp {
 
-constexpr int ST_TW = 32, ST_TH = 8;
-constexpr int ST_IW = ST_TW * 2 + 1, ST_IH = ST_TH * 2 + 1;   // 65 x 17
-constexpr int ST_IWP = ST_IW + 2;                              // pad row pitch (odd*... keeps 2-way max)
+constexpr int ST_TW = 64, ST_TH = 8;                          // output tile; each thread owns 2 x-adjacent pixels
+constexpr int ST_IW = ST_TW * 2 + 1, ST_IH = ST_TH * 2 + 1;   // 129 x 17 input patch (stride 2, pad 1)
+constexpr int ST_IWP = ST_IW + 3;                              // row pitch 132 floats
 
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 stem_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
             __half* __restrict__ y, int H, int W, int flip_x) {
-    __shared__ float s_in[3][ST_IH][ST_IWP];
+    __shared__ __align__(16) float s_in[3][ST_IH][ST_IWP];
     __shared__ __align__(16) float s_w[27][32];   // [tap][co]
-    __shared__ float s_b[32];
+    __shared__ __align__(16) float s_b[32];
     const int Ho = H / 2, Wo = W / 2;
     const int n = blockIdx.z;
     const int ox0 = blockIdx.x * ST_TW, oy0 = blockIdx.y * ST_TH;
@@ -32,50 +33,86 @@ stem_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, const float
     }
     if (threadIdx.x < 32) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
     const TIn* xn = x + (size_t)n * 3 * H * W;
-    for (int i = threadIdx.x; i < 3 * ST_IH * ST_IW; i += 256) {
-        const int c = i / (ST_IH * ST_IW);
-        const int r = (i / ST_IW) % ST_IH;
-        const int col = i % ST_IW;
-        const int gy = iy0 + r, gx = ix0 + col;
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = (float)xn[((size_t)c * H + gy) * W + (flip_x ? W - 1 - gx : gx)];
-        s_in[c][r][col] = v;
+    // patch load: 3*17 rows of 129 floats; 8 independent global loads in flight per thread
+    constexpr int NELEM = 3 * ST_IH * ST_IW;
+    for (int i0 = threadIdx.x; i0 < NELEM; i0 += 256 * 8) {
+        float tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            float v = 0.f;
+            if (i < NELEM) {
+                const int c = i / (ST_IH * ST_IW);
+                const int rem = i - c * (ST_IH * ST_IW);
+                const int r = rem / ST_IW, col = rem - r * ST_IW;
+                const int gy = iy0 + r, gx = ix0 + col;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+                    v = (float)xn[((size_t)c * H + gy) * W + (flip_x ? W - 1 - gx : gx)];
+            }
+            tmp[u] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            if (i < NELEM) {
+                const int c = i / (ST_IH * ST_IW);
+                const int rem = i - c * (ST_IH * ST_IW);
+                const int r = rem / ST_IW, col = rem - r * ST_IW;
+                s_in[c][r][col] = tmp[u];
+            }
+        }
     }
     __syncthreads();
 
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int ox = ox0 + lx, oy = oy0 + ly;
-    float acc[32];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;    // pixels (2*lx, 2*lx+1) of row ly
+    float acc0[32], acc1[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = s_b[i];
+    for (int i = 0; i < 32; ++i) acc0[i] = acc1[i] = s_b[i];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky) {
+            // the two pixels need input columns 4*lx .. 4*lx+4
+            const float* row = &s_in[c][2 * ly + ky][4 * lx];
+            const float4 a = *reinterpret_cast<const float4*>(row);
+            const float e = row[4];
+            const float in0[3] = {a.x, a.y, a.z};
+            const float in1[3] = {a.z, a.w, e};
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float v = s_in[c][2 * ly + ky][2 * lx + kx];
                 const float4* wr = reinterpret_cast<const float4*>(s_w[c * 9 + ky * 3 + kx]);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     const float4 wv = wr[g];
-                    acc[4 * g + 0] = fmaf(v, wv.x, acc[4 * g + 0]);
-                    acc[4 * g + 1] = fmaf(v, wv.y, acc[4 * g + 1]);
-                    acc[4 * g + 2] = fmaf(v, wv.z, acc[4 * g + 2]);
-                    acc[4 * g + 3] = fmaf(v, wv.w, acc[4 * g + 3]);
+                    acc0[4 * g + 0] = fmaf(in0[kx], wv.x, acc0[4 * g + 0]);
+                    acc0[4 * g + 1] = fmaf(in0[kx], wv.y, acc0[4 * g + 1]);
+                    acc0[4 * g + 2] = fmaf(in0[kx], wv.z, acc0[4 * g + 2]);
+                    acc0[4 * g + 3] = fmaf(in0[kx], wv.w, acc0[4 * g + 3]);
+                    acc1[4 * g + 0] = fmaf(in1[kx], wv.x, acc1[4 * g + 0]);
+                    acc1[4 * g + 1] = fmaf(in1[kx], wv.y, acc1[4 * g + 1]);
+                    acc1[4 * g + 2] = fmaf(in1[kx], wv.z, acc1[4 * g + 2]);
+                    acc1[4 * g + 3] = fmaf(in1[kx], wv.w, acc1[4 * g + 3]);
                 }
             }
-    if (ox < Wo && oy < Ho) {
-        uint4* op = reinterpret_cast<uint4*>(y + (((size_t)n * Ho + oy) * Wo + ox) * 32);
+        }
+    const int oy = oy0 + ly;
+    if (oy < Ho) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            __half2* h = reinterpret_cast<__half2*>(&o);
+        for (int p = 0; p < 2; ++p) {
+            const int ox = ox0 + 2 * lx + p;
+            if (ox >= Wo) continue;
+            const float* acc = p ? acc1 : acc0;
+            uint4* op = reinterpret_cast<uint4*>(y + (((size_t)n * Ho + oy) * Wo + ox) * 32);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                h[i] = __floats2half2_rn(fminf(fmaxf(acc[8 * g + 2 * i], 0.f), 6.f),
-                                         fminf(fmaxf(acc[8 * g + 2 * i + 1], 0.f), 6.f));
-            op[g] = o;
+            for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    h[i] = __floats2half2_rn(fminf(fmaxf(acc[8 * g + 2 * i], 0.f), 6.f),
+                                             fminf(fmaxf(acc[8 * g + 2 * i + 1], 0.f), 6.f));
+                op[g] = o;
+            }
         }
     }
 }
