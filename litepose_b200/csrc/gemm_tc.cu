@@ -209,17 +209,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const bool issuer = (threadIdx.x == 64);
                 const int ncols = min(p.n_tile, p.N - chunk * p.n_tile);       // valid columns of this chunk
                 const int nsub = (ncols + 63) >> 6;
-                if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging free again
+                // staging: 4 sub-tile slots; tiles of <= 128 columns alternate between two slot groups so the TMA store
+                // of tile i drains while tile i+1 is being converted (one store group may stay in flight)
+                const int nsub_max = (p.n_tile + 63) >> 6;
+                const bool dbuf = nsub_max <= 2;
+                uint8_t* sStage = sOut + ((dbuf && (it & 1)) ? 2 * OUT_SUB : 0);
+                if (issuer) {
+                    if (dbuf) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (p.residual && issuer) {   // residual tile is fetched while this tile's MMAs are still running
                     mbar_expect_tx(&bars->res_full, nsub * OUT_SUB);
                     for (int g = 0; g < nsub; ++g)
-                        tma_load_2d(sOut + g * OUT_SUB, &mapRes, &bars->res_full, chunk * p.n_tile + g * 64, mt * BM);
+                        tma_load_2d(sStage + g * OUT_SUB, &mapRes, &bars->res_full, chunk * p.n_tile + g * 64, mt * BM);
                 }
                 mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
                 tc_fence_after();
                 if (p.residual) mbar_wait(&bars->res_full, it & 1);
-                uint8_t* srow = sOut + row * 128;
+                uint8_t* srow = sStage + row * 128;
                 for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
                     tc_ld16(taddr + c0, r);
                     tc_wait_ld();
@@ -277,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int g = 0; g < nsub; ++g) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                          reinterpret_cast<uint64_t>(&mapOut)),
-                                     "r"(smem_u32(sOut + g * OUT_SUB)), "r"(chunk * p.n_tile + g * 64), "r"(mt * BM)
+                                     "r"(smem_u32(sStage + g * OUT_SUB)), "r"(chunk * p.n_tile + g * 64), "r"(mt * BM)
                                      : "memory");
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -4,10 +4,10 @@
 // Canonical order (torch.topk's tie order is unspecified): value desc, flat index asc over
 // survivors with value > 0; unused slots are (0.0f, index 0)  -- same rule as oracle/group_ref.py.
 //
-// HBM-bound: det is read once (algorithmic bytes 4*N*J*H*W).  Kernel 1: one CTA per strip of
-// rows of one plane; separable window max in shared memory, then K rounds of a block-wide
-// arg-max over 64-bit keys (value bits << 32 | ~index) using warp-shuffle reductions.
-// Kernel 2: one warp per plane merges the per-strip sorted lists and gathers the tags.
+// HBM-bound: det is read once (algorithmic bytes 4*N*J*H*W).  Kernel 1: one CTA per band of rows of one
+// plane keeps a running sorted top-K of 64-bit keys (value bits << 32 | ~index); the window maximum is
+// evaluated only for pixels that reach the current K-th value; candidates are compacted with warp
+// ballots and merged by one warp.  Kernel 2: one warp per plane merges the per-band lists and gathers tags.
 #include "common.cuh"
 
 namespace lp {
@@ -54,90 +54,103 @@ __device__ __forceinline__ int topk_insert(unsigned long long* s_top, int ntop, 
     return nnew;
 }
 
-// partial: [N*J][bands][K] keys (sorted, 0 = empty).  One CTA walks TK_SPB strips of SR rows of one plane and
-// keeps a running top-K; only NMS survivors above the current K-th key are ever inserted, so after the first few
-// rows the selection cost vanishes and the kernel streams at memory speed.
+constexpr int TK_RB = 4;   // rows evaluated per barrier round (they share one threshold)
+
+// partial: [N*J][bands][K] keys (sorted, 0 = empty).  One CTA walks TK_SPB strips of SR rows of one plane and keeps a
+// running top-K.  A pixel can only enter the list if its value reaches the current K-th value, so the k x k window
+// maximum (the NMS test) is evaluated ONLY for those pixels: once the list is full the kernel is a plain streaming
+// pass (one shared-memory read and one compare per pixel) and runs at memory speed.
 __global__ void __launch_bounds__(TK_THREADS)
 nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*window radius*/, int SR, int K,
                       unsigned long long* __restrict__ partial) {
     extern __shared__ __align__(16) float sm[];
     const int plane = blockIdx.y;
     const int band = blockIdx.x, nbands = gridDim.x;
-    float* s_val = sm;                             // [SR+2R][W] raw values
-    float* s_hmax = sm + (size_t)(SR + 2 * R) * W; // [SR+2R][W] horizontal window max
+    float* s_val = sm;                             // [SR+2R][W] raw values (out-of-image rows hold -inf)
     __shared__ unsigned long long s_top[TK_MAXK];
-    __shared__ unsigned long long s_cand[TK_MAXW];
-    __shared__ int s_ncand[2], s_ntop;   // candidate counter double-buffered by row parity (see barrier note)
+    __shared__ unsigned long long s_cand[TK_RB * TK_MAXW];
+    __shared__ int s_ncand[2], s_ntop;             // candidate counter double-buffered by round parity
     const float* p = det + (size_t)plane * H * W;
     const float NEG_INF = __int_as_float(0xff800000);
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { s_ncand[0] = 0; s_ncand[1] = 0; s_ntop = 0; }
-    int rowpar = 0;
     if (threadIdx.x < TK_MAXK) s_top[threadIdx.x] = 0ull;
+    int par = 0;
+    const bool vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 
     for (int st = 0; st < TK_SPB; ++st) {
         const int y0 = (band * TK_SPB + st) * SR;
         if (y0 >= H) break;
         const int rows = min(SR, H - y0);
-        const int hrows = rows + 2 * R;            // rows incl. halo (out-of-image rows hold -inf)
+        const int hrows = rows + 2 * R;
         __syncthreads();                           // previous strip fully consumed
-        // batched loads: 8 independent global loads in flight per thread before the first shared store
-        for (int x = threadIdx.x; x < W; x += TK_THREADS) {
-            for (int r0 = 0; r0 < hrows; r0 += 8) {
-                float tmp[8];
+        if (vec) {
+            const int w4 = W >> 2;
+            for (int i = threadIdx.x; i < hrows * w4; i += TK_THREADS * 4) {
+                float4 tmp[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int gy = y0 - R + r0 + u;
-                    tmp[u] = (r0 + u < hrows && gy >= 0 && gy < H) ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
+                for (int u = 0; u < 4; ++u) {
+                    const int q = i + u * TK_THREADS;
+                    const int r = q / w4, c = q - r * w4;
+                    const int gy = y0 - R + r;
+                    tmp[u] = (q < hrows * w4 && gy >= 0 && gy < H)
+                                 ? __ldg(reinterpret_cast<const float4*>(p + (size_t)gy * W) + c)
+                                 : make_float4(NEG_INF, NEG_INF, NEG_INF, NEG_INF);
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (r0 + u < hrows) s_val[(r0 + u) * W + x] = tmp[u];
+                for (int u = 0; u < 4; ++u) {
+                    const int q = i + u * TK_THREADS;
+                    if (q < hrows * w4) reinterpret_cast<float4*>(s_val)[q] = tmp[u];
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < hrows * W; i += TK_THREADS) {
+                const int r = i / W, x = i - r * W;
+                const int gy = y0 - R + r;
+                s_val[i] = (gy >= 0 && gy < H) ? __ldg(p + (size_t)gy * W + x) : NEG_INF;
             }
         }
         __syncthreads();
-        for (int r = 0; r < hrows; ++r)
-            for (int x = threadIdx.x; x < W; x += TK_THREADS) {
-                float m = NEG_INF;
-                const int xa = max(x - R, 0), xb = min(x + R, W - 1);
-                for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[r * W + xx]);
-                s_hmax[r * W + x] = m;
-            }
-        __syncthreads();
-        for (int r = 0; r < rows; ++r, rowpar ^= 1) {
-            // threshold = current K-th key (0 while the list is not full)
+        for (int r0 = 0; r0 < rows; r0 += TK_RB, par ^= 1) {
             const int ntop0 = s_ntop;
             const unsigned long long thr = ntop0 >= K ? s_top[K - 1] : 0ull;
-            for (int x0 = 0; x0 < W; x0 += TK_THREADS) {
-                const int x = x0 + threadIdx.x;
-                unsigned long long key = 0ull;
-                if (x < W) {
-                    float m = NEG_INF;
-                    for (int d = 0; d <= 2 * R; ++d) m = fmaxf(m, s_hmax[(r + d) * W + x]);
-                    const float v = s_val[(r + R) * W + x];
-                    if (v == m && v > 0.f) {
-                        const unsigned idx = (unsigned)((y0 + r) * W + x);
-                        key = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
+            const float thr_v = __uint_as_float((unsigned)(thr >> 32));          // 0 while the list is not full
+            const int rend = min(r0 + TK_RB, rows);
+            for (int r = r0; r < rend; ++r)
+                for (int x0 = 0; x0 < W; x0 += TK_THREADS) {
+                    const int x = x0 + threadIdx.x;
+                    unsigned long long key = 0ull;
+                    if (x < W) {
+                        const float v = s_val[(r + R) * W + x];
+                        if (v > 0.f && v >= thr_v) {                              // rare once the list is full
+                            float m = NEG_INF;
+                            const int xa = max(x - R, 0), xb = min(x + R, W - 1);
+                            for (int d = 0; d <= 2 * R; ++d)
+                                for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[(r + d) * W + xx]);
+                            if (v == m) {
+                                const unsigned idx = (unsigned)((y0 + r) * W + x);
+                                key = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
+                            }
+                        }
+                    }
+                    const bool cand = key > thr;
+                    const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                    if (bal) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_ncand[par], __popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (cand) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
                     }
                 }
-                const bool cand = key > thr;
-                const unsigned bal = __ballot_sync(0xffffffffu, cand);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_ncand[rowpar], __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (cand) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
-                }
-            }
             __syncthreads();
-            // block-uniform: this row's counter is not touched again before the next row's barrier (the next row
+            // block-uniform: this round's counter is not touched again before the next round's barrier (the next round
             // counts into the other slot), so every thread reads the same value here
-            if (s_ncand[rowpar]) {
+            if (s_ncand[par]) {
                 if (threadIdx.x < 32) {
-                    const int nc = s_ncand[rowpar];
+                    const int nc = s_ncand[par];
                     int ntop = s_ntop;
                     for (int c = 0; c < nc; ++c) ntop = topk_insert(s_top, ntop, K, s_cand[c], lane);
-                    if (lane == 0) { s_ntop = ntop; s_ncand[rowpar] = 0; }
+                    if (lane == 0) { s_ntop = ntop; s_ncand[par] = 0; }
                 }
                 __syncthreads();
             }
@@ -222,7 +235,7 @@ extern "C" int lp_nms_topk_f32(const float* det, const float* tag, int N, int J,
         set_error("lp_nms_topk_f32: workspace %zu < required %zu bytes", workspace_bytes, need);
         return LP_ERR_CAPACITY;
     }
-    const size_t smem = (size_t)2 * (sr + 2 * R) * W * sizeof(float);
+    const size_t smem = (size_t)(sr + 2 * R) * W * sizeof(float);
     LP_CHECK_ARG(smem <= 200 * 1024, "lp_nms_topk_f32: W=%d too wide for the strip buffers", W);
     cudaError_t e = cudaFuncSetAttribute((const void*)nms_topk_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
