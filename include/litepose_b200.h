@@ -95,6 +95,15 @@ int lp_pw1x1_pack(const uint16_t* w_f16 /*[N][K] host*/, const float* bias /*[N]
 int lp_pw1x1_f16(const void* a, const void* w_packed, const float* bias_packed, const void* residual,
                  void* out, int M, int K, int N, int act, lp_stream_t stream);
 
+/* ---- M2 fused: depthwise 7x7 stride 1 (+bias +ReLU6) -> pointwise projection (+bias)(+residual)
+ * (InvBottleneck.depth_conv + point_conv + identity add, lib/models/layers/layers.py:100-118) in one
+ * kernel: the expanded depthwise output stays in shared memory as the tcgen05 A operand.
+ * x [N,H,W,Ce] NHWC fp16; w_dw fp16 [49][Ce]; b_dw fp32 [Ce]; w_proj_packed / b_proj_packed from
+ * lp_pw1x1_pack(K = Ce, N = Co); residual/out [N,H,W,Co] fp16.  Ce % 8 == 0, Co % 8 == 0, Co <= 160. */
+int lp_dw7_project_f16(const void* x, const void* w_dw, const float* b_dw, const void* w_proj_packed,
+                       const float* b_proj_packed, const void* residual, void* out, int N, int H, int W,
+                       int Ce, int Co, lp_stream_t stream);
+
 /* ---- M3: fusion deconv level ----------------------------------------------
  * out = ReLU(ConvT4x4s2p1(refined) + ConvT4x4s2p1(raw) + bias), one kernel.
  * refined NHWC fp16 [N,H,W,Cr], raw [N,H,W,Cw], out [N,2H,2W,Co].

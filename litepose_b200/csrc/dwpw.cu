@@ -1,0 +1,348 @@
+// Fused depthwise 7x7 (stride 1) + ReLU6 + pointwise projection (+ residual) of an inverted-residual block
+// (reference lib/models/layers/layers.py:100-118: depth_conv -> point_conv -> optional identity add).
+//
+// Unfused, the 6x-expanded tensor is written by the depthwise kernel and read back by the projection GEMM; here it
+// never leaves the SM.  Per CTA (persistent over 16x16-pixel output tiles):
+//   warp 8 (1 thread)  TMA producer: haloed 22x22x32-channel input slabs (hardware zero fill = conv padding) into a
+//                      3-deep ring, projection-weight K blocks into a 2-deep ring
+//   warps 0-7          depthwise on the CUDA cores: one 4x4 micro-block x channel pair per thread per slab (same
+//                      mixed-precision FHFMA inner loop and mirrored conflict-free LDS as dwconv.cu), results written
+//                      as fp16 straight into the 128B-swizzled K-major A-operand tiles in shared memory
+//   warp 9 (1 thread)  tcgen05.mma: D[256 px x Co] += A[256 x 64 ch] * Wp^T per 64-channel K block, fp32 in TMEM
+//   warps 0-7          epilogue: tcgen05.ld, + folded-BN bias (+ residual row), fp16, 16-byte stores of whole rows
+// HBM traffic per block: read N*H*W*Ce*2 (+ N*H*W*Co*2 residual), write N*H*W*Co*2  -- the depthwise output
+// (N*H*W*Ce*2 written + read again) is gone; the kernel is bound by the FMA pipe (2*49 flop per expanded element).
+#include "common.cuh"
+
+namespace lp {
+
+constexpr int FP_T = 16;                         // output tile side
+constexpr int FP_I = FP_T + 6;                   // haloed input side (k = 7)
+constexpr int FP_CB = 32;                        // channels per slab
+constexpr int FP_IN_BYTES = FP_I * FP_I * FP_CB * 2;          // 30976
+constexpr int FP_IN_STRIDE = 31744;                           // ring pitch (multiple of 1024)
+constexpr int FP_NIN = 3;
+constexpr int FP_A_TILE = 128 * 64 * 2;                       // one M-tile x one 64-channel K block, 16 KiB
+constexpr int FP_NB = 2;
+constexpr int FP_B_BYTES = 160 * 64 * 2;                      // Co <= 160
+constexpr int FP_THREADS = 320;
+constexpr size_t FP_SMEM = (size_t)FP_NIN * FP_IN_STRIDE + 4 * FP_A_TILE + FP_NB * FP_B_BYTES + 1024 + 1024;
+
+struct FpBars {
+    uint64_t in_full[FP_NIN], in_empty[FP_NIN];
+    uint64_t a_full[2], a_empty[2];
+    uint64_t b_full[FP_NB], b_empty[FP_NB];
+    uint64_t tmem_full, tmem_empty;
+    uint32_t tmem_base, pad;
+};
+
+struct FpParams {
+    int N, H, W, Ce, Co, n_tile;      // n_tile = round_up(Co, 16)
+    int tiles_x, tiles_y, num_tiles;
+    int nslabs, nkb;
+    const __half* w_dw;               // [49][Ce]
+    const float* b_dw;                // [Ce]
+    const float* b_pj;                // packed, n_tile
+    const __half* residual;           // [N,H,W,Co] or null
+    __half* out;                      // [N,H,W,Co]
+};
+
+__device__ __forceinline__ float fp_fhfma(unsigned short a, unsigned short b, float c) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned short fp_lo(__half2 v) { return __half_as_ushort(__low2half(v)); }
+__device__ __forceinline__ unsigned short fp_hi(__half2 v) { return __half_as_ushort(__high2half(v)); }
+
+__global__ void __launch_bounds__(FP_THREADS, 1)
+dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                   const __grid_constant__ FpParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sIn = smem;                                         // FP_NIN x [22][22][32] fp16
+    uint8_t* sA = smem + FP_NIN * FP_IN_STRIDE;                  // [kbuf 2][mtile 2] x 16 KiB, 128B-swizzled
+    uint8_t* sB = sA + 4 * FP_A_TILE;                            // FP_NB x [n_tile][64] fp16, 128B-swizzled
+    float* sBias = reinterpret_cast<float*>(sB + FP_NB * FP_B_BYTES);
+    FpBars* bars = reinterpret_cast<FpBars*>(sBias + 192);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int K = 7;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+        for (int i = 0; i < FP_NIN; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 8); mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < FP_NB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        mbar_init(&bars->tmem_full, 1);
+        mbar_init(&bars->tmem_empty, 8);
+        fence_barrier_init();
+    }
+    if (warp == 9) {
+        tc_alloc(&bars->tmem_base, 512);
+        tc_relinquish();
+    }
+    for (int i = threadIdx.x; i < p.n_tile; i += FP_THREADS) sBias[i] = p.b_pj ? p.b_pj[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t is = 0, iph = 0, bs = 0, bph = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
+                for (int s = 0; s < p.nslabs; ++s) {
+                    if ((s & 1) == 0) {   // projection weights of K block s/2
+                        mbar_wait(&bars->b_empty[bs], bph ^ 1);
+                        mbar_expect_tx(&bars->b_full[bs], p.n_tile * 128);
+                        tma_load_2d(sB + bs * FP_B_BYTES, &map_w, &bars->b_full[bs], 0, (s >> 1) * p.n_tile);
+                        if (++bs == FP_NB) { bs = 0; bph ^= 1; }
+                    }
+                    mbar_wait(&bars->in_empty[is], iph ^ 1);
+                    mbar_expect_tx(&bars->in_full[is], FP_IN_BYTES);
+                    tma_load_4d(sIn + is * FP_IN_STRIDE, &map_x, &bars->in_full[is], s * FP_CB, tx * FP_T - 3,
+                                ty * FP_T - 3, n);
+                    if (++is == FP_NIN) { is = 0; iph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, p.n_tile);
+            uint32_t bs = 0, bph = 0, kbc = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                mbar_wait(&bars->tmem_empty, (it & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
+                    const uint32_t kbuf = kbc & 1;
+                    mbar_wait(&bars->a_full[kbuf], (kbc >> 1) & 1);
+                    mbar_wait(&bars->b_full[bs], bph);
+                    tc_fence_after();
+                    const int chans = min(64, p.Ce - kb * 64);
+                    const int k16 = (chans + 15) >> 4;
+                    const uint32_t b_base = smem_u32(sB + bs * FP_B_BYTES);
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint32_t a_base = smem_u32(sA + (kbuf * 2 + mt) * FP_A_TILE);
+                        for (int k = 0; k < k16; ++k)
+                            tc_mma_f16(tmem_base + mt * p.n_tile, umma_desc_sw128(a_base + k * 32),
+                                       umma_desc_sw128(b_base + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&bars->a_empty[kbuf]);
+                    tc_commit(&bars->b_empty[bs]);
+                    if (++bs == FP_NB) { bs = 0; bph ^= 1; }
+                }
+                tc_commit(&bars->tmem_full);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ depthwise warps + epilogue
+        const int cp = threadIdx.x & 15;
+        const int sub = (threadIdx.x >> 4) & 1;
+        const bool mir = sub != 0;
+        const int blk = (warp << 1) | sub;                 // 16 micro-blocks: 4 x 4 of 4x4 pixels
+        const int by = blk >> 2, bx = blk & 3;
+        const int oy = by * 4, ox = bx * 4;
+        const int cstep = mir ? -(FP_CB / 2) : (FP_CB / 2);
+        uint32_t is = 0, iph = 0, kbc = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
+            for (int s = 0; s < p.nslabs; ++s) {
+                const int ch = s * FP_CB + 2 * cp;
+                const bool ch_ok = ch < p.Ce;
+                // weights of this slab for my channel pair (tap-major [49][Ce]); mirrored lanes read kx reversed
+                __half2 wreg[K * K];
+                {
+                    const __half* wb = p.w_dw + ch + (mir ? (K - 1) * p.Ce : 0);
+                    const int wstep = mir ? -p.Ce : p.Ce;
+#pragma unroll
+                    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < K; ++kx)
+                            wreg[ky * K + kx] = ch_ok ? *reinterpret_cast<const __half2*>(wb + ky * K * p.Ce + kx * wstep)
+                                                      : __floats2half2_rn(0.f, 0.f);
+                }
+                float2 b2 = make_float2(0.f, 0.f);
+                if (ch_ok && p.b_dw) b2 = make_float2(p.b_dw[ch], p.b_dw[ch + 1]);
+                float2 acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = b2;
+
+                mbar_wait(&bars->in_full[is], iph);
+                const __half2* tile_in = reinterpret_cast<const __half2*>(sIn + is * FP_IN_STRIDE);
+                const __half2* base = tile_in + (oy * FP_I + ox + (mir ? 9 : 0)) * (FP_CB / 2) + cp;
+#pragma unroll
+                for (int r = 0; r < 10; ++r) {
+                    __half2 in[10];
+#pragma unroll
+                    for (int c = 0; c < 10; ++c) in[c] = base[r * FP_I * (FP_CB / 2) + c * cstep];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int ky = r - i;
+                        if (ky >= 0 && ky < K) {
+#pragma unroll
+                            for (int kx = 0; kx < K; ++kx) {
+                                const __half2 wv = wreg[ky * K + kx];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    acc[i][j].x = fp_fhfma(fp_lo(in[j + kx]), fp_lo(wv), acc[i][j].x);
+                                    acc[i][j].y = fp_fhfma(fp_hi(in[j + kx]), fp_hi(wv), acc[i][j].y);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->in_empty[is]);
+                if (++is == FP_NIN) { is = 0; iph ^= 1; }
+
+                // ReLU6, fp16, into the swizzled A tile: row = pixel, 16-byte chunk j holds channels 8j..8j+7 of the K block
+                const uint32_t kbuf = kbc & 1;
+                if ((s & 1) == 0) mbar_wait(&bars->a_empty[kbuf], ((kbc >> 1) & 1) ^ 1);
+                uint8_t* a_mt = sA + (kbuf * 2 + (by >> 1)) * FP_A_TILE;
+                const int jch = ((s & 1) << 2) | (cp >> 2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = ((oy + i) & 7) * 16 + ox + (mir ? 3 - j : j);     // row inside the M-tile
+                        const __half2 v = __floats2half2_rn(fminf(fmaxf(acc[i][j].x, 0.f), 6.f),
+                                                            fminf(fmaxf(acc[i][j].y, 0.f), 6.f));
+                        *reinterpret_cast<__half2*>(a_mt + r * 128 + ((jch ^ (r & 7)) << 4) + ((cp & 3) << 2)) = v;
+                    }
+                if ((s & 1) || s == p.nslabs - 1) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->a_full[kbuf]);
+                    ++kbc;
+                }
+            }
+            // ---- epilogue: accumulator row = pixel (mt = warp>>2, row = (warp&3)*32 + lane)
+            mbar_wait(&bars->tmem_full, it & 1);
+            tc_fence_after();
+            {
+                const int mt = warp >> 2, row = (warp & 3) * 32 + lane;
+                const int py = mt * 8 + (row >> 4), px = row & 15;
+                const int gy = ty * FP_T + py, gx = tx * FP_T + px;
+                const bool valid = gy < p.H && gx < p.W;
+                const size_t off = (((size_t)n * p.H + gy) * p.W + gx) * p.Co;
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + mt * p.n_tile;
+                uint32_t r[16];
+                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                    tc_ld16(taddr + c0, r);
+                    tc_wait_ld();
+                    if (valid && c0 < p.Co) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBias[c0 + i];
+                        const bool two = (c0 + 8) < p.Co;
+                        if (p.residual) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c0);
+                            const uint4 ra = __ldg(rp);
+                            const __half2* h = reinterpret_cast<const __half2*>(&ra);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(h[i]);
+                                v[2 * i] += f.x;
+                                v[2 * i + 1] += f.y;
+                            }
+                            if (two) {
+                                const uint4 rb = __ldg(rp + 1);
+                                const __half2* g = reinterpret_cast<const __half2*>(&rb);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f = __half22float2(g[i]);
+                                    v[8 + 2 * i] += f.x;
+                                    v[8 + 2 * i + 1] += f.y;
+                                }
+                            }
+                        }
+                        uint4 o0, o1;
+                        __half2* ph0 = reinterpret_cast<__half2*>(&o0);
+                        __half2* ph1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            ph0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                            ph1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(p.out + off + c0);
+                        op[0] = o0;
+                        if (two) op[1] = o1;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+// Fused depthwise-7x7(stride 1, +bias +ReLU6) -> pointwise projection (+bias, +residual).
+// x [N,H,W,Ce] fp16 NHWC; w_dw tap-major [49][Ce]; w_proj_packed / b_proj_packed from lp_pw1x1_pack(K=Ce, N=Co);
+// out [N,H,W,Co].  Ce % 8 == 0, Co % 8 == 0, Co <= 160.
+extern "C" int lp_dw7_project_f16(const void* x, const void* w_dw, const float* b_dw, const void* w_proj_packed,
+                                  const float* b_proj_packed, const void* residual, void* out, int N, int H, int W,
+                                  int Ce, int Co, lp_stream_t stream) {
+    LP_CHECK_ARG(x && w_dw && w_proj_packed && out, "lp_dw7_project_f16: null pointer");
+    LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && Ce >= 8 && Ce % 8 == 0 && Co >= 8 && Co % 8 == 0 && Co <= 160,
+                 "lp_dw7_project_f16: bad shape N=%d H=%d W=%d Ce=%d Co=%d (Co <= 160)", N, H, W, Ce, Co);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w_proj_packed) |
+         reinterpret_cast<uintptr_t>(residual)) & 15) {
+        set_error("lp_dw7_project_f16: pointers must be 16-byte aligned");
+        return LP_ERR_ALIGN;
+    }
+    FpParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.H = H; p.W = W; p.Ce = Ce; p.Co = Co;
+    p.n_tile = (Co + 15) / 16 * 16;
+    p.tiles_x = (W + FP_T - 1) / FP_T;
+    p.tiles_y = (H + FP_T - 1) / FP_T;
+    p.num_tiles = p.tiles_x * p.tiles_y * N;
+    p.nslabs = (Ce + FP_CB - 1) / FP_CB;
+    p.nkb = (Ce + 63) / 64;
+    p.w_dw = reinterpret_cast<const __half*>(w_dw);
+    p.b_dw = b_dw;
+    p.b_pj = b_proj_packed;
+    p.residual = reinterpret_cast<const __half*>(residual);
+    p.out = reinterpret_cast<__half*>(out);
+    CUtensorMap mx, mw;
+    {
+        uint64_t dims[4] = {(uint64_t)Ce, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t strides[3] = {(uint64_t)Ce * 2, (uint64_t)W * Ce * 2, (uint64_t)H * W * Ce * 2};
+        uint32_t box[4] = {(uint32_t)FP_CB, (uint32_t)FP_I, (uint32_t)FP_I, 1u};
+        int rc = make_tmap(&mx, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        // packed projection weights: [kb][n_tile][64] (lp_pw1x1_pack with a single N chunk since Co <= 160)
+        uint64_t d2[2] = {64u, (uint64_t)p.nkb * p.n_tile};
+        uint64_t s2[1] = {128u};
+        uint32_t b2[2] = {64u, (uint32_t)p.n_tile};
+        rc = make_tmap(&mw, w_proj_packed, 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void*)dw7_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FP_SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw7_project)");
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    dw7_project_kernel<<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(mx, mw, p);
+    LP_LAUNCH_CHECK("dw7_project_kernel");
+    return LP_OK;
+}

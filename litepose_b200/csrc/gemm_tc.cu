@@ -23,7 +23,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;    // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;   // 32 KiB
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;        // MODE_PW (plus OUT_BYTES of output staging)
+constexpr int STAGES_NOSTAGE = 4; // MODE_DECONV / MODE_HEAD (no staging buffer)
+constexpr int MAX_STAGES = 4;
 constexpr int OUT_SUB = 128 * 64 * 2;   // one 128-row x 64-column fp16 output sub-tile (128B-swizzled), 16 KiB
 constexpr int OUT_BYTES = 4 * OUT_SUB;  // staging for up to 256 output columns
 constexpr int MAX_STEPS = 48;
@@ -61,8 +63,8 @@ struct GemmParams {
 };
 
 struct __align__(8) GemmBarriers {
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
+    uint64_t full[MAX_STAGES];
+    uint64_t empty[MAX_STAGES];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint64_t res_full;
@@ -78,10 +80,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                const __grid_constant__ CUtensorMap mapRes, const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NST = (MODE == MODE_PW) ? STAGES : STAGES_NOSTAGE;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_BYTES;
-    uint8_t* sOut = smem + STAGES * (A_BYTES + B_BYTES);   // MODE_PW: swizzled output / residual staging
-    float* sBias = reinterpret_cast<float*>(sOut + OUT_BYTES);
+    uint8_t* sB = smem + NST * A_BYTES;
+    uint8_t* sOut = smem + NST * (A_BYTES + B_BYTES);      // MODE_PW: swizzled output / residual staging
+    float* sBias = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + OUT_BYTES);
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sBias + MAX_BIAS);
 
     const int warp = threadIdx.x >> 5;
@@ -96,7 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (p.residual) tma_prefetch_desc(&mapRes);
         }
         mbar_init(&bars->res_full, 1);
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < NST; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->empty[i], 1);
         }
@@ -149,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         tma_load_2d(b_dst + j * p.n_tile * (BK * 2), &mapB, &bars->full[stage], 0,
                                     (chunk * p.total_bt + st.bt0 + j) * p.n_tile);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -181,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         used |= 1u << acc;
                     }
                     tc_commit(&bars->empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&bars->tmem_full[buf]);
             }

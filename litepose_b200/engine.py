@@ -45,6 +45,8 @@ class LitePoseEngine(object):
         self.arch = arch
         self.plans = {}
         self.use_graphs = False
+        import os
+        self.fuse_dw_project = os.environ.get("LP_FUSE_DW_PROJECT", "1") != "0"
         sd = {k: v.detach() for k, v in state_dict.items()}
         self._prep(sd)
 
@@ -174,14 +176,21 @@ class LitePoseEngine(object):
             ops.append(_Op("inv", lib.lp_pw1x1_f16, [cur.data_ptr(), inv["w"].data_ptr(), inv["b"].data_ptr(), None,
                                                       e_buf.data_ptr(), n * ch * cw_, inv["K"], inv["N"],
                                                       _lib.ACT_RELU6]))
-            ops.append(_Op("dw7", lib.lp_dwconv_f16, [e_buf.data_ptr(), dw["w"].data_ptr(), dw["b"].data_ptr(),
-                                                       d_buf.data_ptr(), n, dw["C"], ch, cw_, dw["k"], blk["stride"],
-                                                       _lib.ACT_RELU6]))
             out = buf(n, oh, ow, pc["N"])
             keep.append(out)
-            ops.append(_Op("pc", lib.lp_pw1x1_f16, [d_buf.data_ptr(), pc["w"].data_ptr(), pc["b"].data_ptr(),
-                                                     cur.data_ptr() if blk["res"] else None, out.data_ptr(),
-                                                     n * oh * ow, pc["K"], pc["N"], _lib.ACT_NONE]))
+            if self.fuse_dw_project and blk["stride"] == 1 and dw["k"] == 7 and pc["N"] <= 160:
+                # depthwise + projection (+ identity) in one kernel: the expanded dw output never reaches HBM
+                ops.append(_Op("dw7_project", lib.lp_dw7_project_f16,
+                               [e_buf.data_ptr(), dw["w"].data_ptr(), dw["b"].data_ptr(), pc["w"].data_ptr(),
+                                pc["b"].data_ptr(), cur.data_ptr() if blk["res"] else None, out.data_ptr(), n, ch,
+                                cw_, dw["C"], pc["N"]]))
+            else:
+                ops.append(_Op("dw7", lib.lp_dwconv_f16, [e_buf.data_ptr(), dw["w"].data_ptr(), dw["b"].data_ptr(),
+                                                           d_buf.data_ptr(), n, dw["C"], ch, cw_, dw["k"],
+                                                           blk["stride"], _lib.ACT_RELU6]))
+                ops.append(_Op("pc", lib.lp_pw1x1_f16, [d_buf.data_ptr(), pc["w"].data_ptr(), pc["b"].data_ptr(),
+                                                         cur.data_ptr() if blk["res"] else None, out.data_ptr(),
+                                                         n * oh * ow, pc["K"], pc["N"], _lib.ACT_NONE]))
             cur, ch, cw_ = out, oh, ow
             if blk["last"]:
                 x_list.append((cur, ch, cw_))

@@ -153,3 +153,34 @@ def test_error_codes():
     assert rc == 1
     rc = lib.lp_pw1x1_f16(x.data_ptr(), x.data_ptr(), None, None, x.data_ptr(), 8, 12, 8, 0, None)
     assert rc == 1
+
+
+@pytest.mark.parametrize("n,h,w,ce,co,res", [
+    (2, 32, 32, 96, 16, True), (1, 16, 16, 96, 16, False), (2, 48, 32, 192, 32, True), (1, 32, 32, 288, 48, True),
+    (1, 32, 32, 720, 120, True), (2, 16, 16, 144, 24, True), (1, 20, 40, 432, 72, False), (1, 32, 32, 288, 120, False),
+    (3, 64, 64, 96, 16, True),
+])
+def test_dw7_project_fused(n, h, w, ce, co, res):
+    """fused depthwise-7x7 + projection (+residual) against the unfused fp32 reference"""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(ce + co + h)
+    x = q16(torch.rand(n, ce, h, w, generator=g) * 3.0)
+    wd = q16(torch.randn(ce, 1, 7, 7, generator=g) * 0.15)
+    bd = torch.randn(ce, generator=g) * 0.1
+    wp = q16(torch.randn(co, ce, generator=g) / (ce ** 0.5))
+    bp = torch.randn(co, generator=g) * 0.1
+    r = q16(torch.randn(n, co, h, w, generator=g)) if res else None
+    mid = q16(F.relu6(F.conv2d(x, wd, bd, 1, 3, 1, ce)))
+    ref = F.conv2d(mid, wp.view(co, ce, 1, 1), bp)
+    if res:
+        ref = ref + r
+    wpk, bpk = pack_pw(wp, bp)
+    xd = nhwc16(x)
+    wdd = wd.reshape(ce, 49).t().contiguous().half().cuda()
+    rd = nhwc16(r) if res else None
+    out = torch.full((n, h, w, co), float("nan"), dtype=torch.float16, device="cuda")
+    _lib.check(lib.lp_dw7_project_f16(xd.data_ptr(), wdd.data_ptr(), bd.cuda().data_ptr(), wpk.data_ptr(),
+                                      bpk.data_ptr(), rd.data_ptr() if res else None, out.data_ptr(), n, h, w, ce, co,
+                                      stream()), "dw7_project")
+    torch.cuda.synchronize()
+    tol_check(from_nhwc(out), ref, what="dw7_project ce%d co%d" % (ce, co))
