@@ -3,13 +3,14 @@
 //
 // Unfused, the 6x-expanded tensor is written by the depthwise kernel and read back by the projection GEMM; here it
 // never leaves the SM.  Per CTA (persistent over 16x16-pixel output tiles):
-//   warp 8 (1 thread)  TMA producer: haloed 22x22x32-channel input slabs (hardware zero fill = conv padding) into a
-//                      3-deep ring, projection-weight K blocks into a 2-deep ring
-//   warps 0-7          depthwise on the CUDA cores: one 4x4 micro-block x channel pair per thread per slab (same
+//   warp 16 (1 thread) TMA producer: haloed 22x22x32-channel input slabs (hardware zero fill = conv padding) into a
+//                      4-deep ring, projection-weight K blocks into a 2-deep ring
+//   warps 0-15         depthwise on the CUDA cores, two groups of 8 warps working on the two 32-channel halves of a
+//                      64-channel K block: one 4x4 micro-block x channel pair per thread per slab (same
 //                      mixed-precision FHFMA inner loop and mirrored conflict-free LDS as dwconv.cu), results written
 //                      as fp16 straight into the 128B-swizzled K-major A-operand tiles in shared memory
-//   warp 9 (1 thread)  tcgen05.mma: D[256 px x Co] += A[256 x 64 ch] * Wp^T per 64-channel K block, fp32 in TMEM
-//   warps 0-7          epilogue: tcgen05.ld, + folded-BN bias (+ residual row), fp16, 16-byte stores of whole rows
+//   warp 17 (1 thread) tcgen05.mma: D[256 px x Co] += A[256 x 64 ch] * Wp^T per 64-channel K block, fp32 in TMEM
+//   warps 0-15         epilogue: tcgen05.ld, + folded-BN bias (+ residual row), fp16, 16-byte stores of whole rows
 // HBM traffic per block: read N*H*W*Ce*2 (+ N*H*W*Co*2 residual), write N*H*W*Co*2  -- the depthwise output
 // (N*H*W*Ce*2 written + read again) is gone; the kernel is bound by the FMA pipe (2*49 flop per expanded element).
 #include "common.cuh"
@@ -21,16 +22,17 @@ constexpr int FP_I = FP_T + 6;                   // haloed input side (k = 7)
 constexpr int FP_CB = 32;                        // channels per slab
 constexpr int FP_IN_BYTES = FP_I * FP_I * FP_CB * 2;          // 30976
 constexpr int FP_IN_STRIDE = 31744;                           // ring pitch (multiple of 1024)
-constexpr int FP_NIN = 3;
+constexpr int FP_NIN = 4;                                      // slab ring: even slabs use stages 0/2, odd 1/3
 constexpr int FP_A_TILE = 128 * 64 * 2;                       // one M-tile x one 64-channel K block, 16 KiB
 constexpr int FP_NB = 2;
 constexpr int FP_B_BYTES = 160 * 64 * 2;                      // Co <= 160
-constexpr int FP_THREADS = 320;
-constexpr size_t FP_SMEM = (size_t)FP_NIN * FP_IN_STRIDE + 4 * FP_A_TILE + FP_NB * FP_B_BYTES + 1024 + 1024;
+constexpr int FP_DW_WARPS = 16;                                // two groups of 8: even / odd 32-channel slabs
+constexpr int FP_THREADS = (FP_DW_WARPS + 2) * 32;
+constexpr size_t FP_SMEM = (size_t)FP_NIN * FP_IN_STRIDE + 2 * FP_A_TILE + FP_NB * FP_B_BYTES + 1024 + 1024;
 
 struct FpBars {
     uint64_t in_full[FP_NIN], in_empty[FP_NIN];
-    uint64_t a_full[2], a_empty[2];
+    uint64_t a_full, a_empty;
     uint64_t b_full[FP_NB], b_empty[FP_NB];
     uint64_t tmem_full, tmem_empty;
     uint32_t tmem_base, pad;
@@ -60,8 +62,8 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                    const __grid_constant__ FpParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sIn = smem;                                         // FP_NIN x [22][22][32] fp16
-    uint8_t* sA = smem + FP_NIN * FP_IN_STRIDE;                  // [kbuf 2][mtile 2] x 16 KiB, 128B-swizzled
-    uint8_t* sB = sA + 4 * FP_A_TILE;                            // FP_NB x [n_tile][64] fp16, 128B-swizzled
+    uint8_t* sA = smem + FP_NIN * FP_IN_STRIDE;                  // [mtile 2] x 16 KiB, 128B-swizzled
+    uint8_t* sB = sA + 2 * FP_A_TILE;                            // FP_NB x [n_tile][64] fp16, 128B-swizzled
     float* sBias = reinterpret_cast<float*>(sB + FP_NB * FP_B_BYTES);
     FpBars* bars = reinterpret_cast<FpBars*>(sBias + 192);
 
@@ -72,13 +74,14 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
         for (int i = 0; i < FP_NIN; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 8); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars->a_full[i], 8); mbar_init(&bars->a_empty[i], 1); }
+        mbar_init(&bars->a_full, FP_DW_WARPS);
+        mbar_init(&bars->a_empty, 1);
         for (int i = 0; i < FP_NB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
         mbar_init(&bars->tmem_full, 1);
-        mbar_init(&bars->tmem_empty, 8);
+        mbar_init(&bars->tmem_empty, FP_DW_WARPS);
         fence_barrier_init();
     }
-    if (warp == 9) {
+    if (warp == FP_DW_WARPS + 1) {
         tc_alloc(&bars->tmem_base, 512);
         tc_relinquish();
     }
@@ -88,10 +91,10 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 8) {
+    if (warp == FP_DW_WARPS) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            uint32_t is = 0, iph = 0, bs = 0, bph = 0;
+            uint32_t iu[2] = {0, 0}, bs = 0, bph = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
                 for (int s = 0; s < p.nslabs; ++s) {
@@ -101,15 +104,17 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         tma_load_2d(sB + bs * FP_B_BYTES, &map_w, &bars->b_full[bs], 0, (s >> 1) * p.n_tile);
                         if (++bs == FP_NB) { bs = 0; bph ^= 1; }
                     }
-                    mbar_wait(&bars->in_empty[is], iph ^ 1);
+                    const int g = s & 1;                              // even / odd slab group, stages g and g+2
+                    const uint32_t is = 2 * (iu[g] & 1) + g;
+                    mbar_wait(&bars->in_empty[is], ((iu[g] >> 1) & 1) ^ 1);
                     mbar_expect_tx(&bars->in_full[is], FP_IN_BYTES);
                     tma_load_4d(sIn + is * FP_IN_STRIDE, &map_x, &bars->in_full[is], s * FP_CB, tx * FP_T - 3,
                                 ty * FP_T - 3, n);
-                    if (++is == FP_NIN) { is = 0; iph ^= 1; }
+                    ++iu[g];
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == FP_DW_WARPS + 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(128, p.n_tile);
@@ -119,20 +124,19 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 mbar_wait(&bars->tmem_empty, (it & 1) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
-                    const uint32_t kbuf = kbc & 1;
-                    mbar_wait(&bars->a_full[kbuf], (kbc >> 1) & 1);
+                    mbar_wait(&bars->a_full, kbc & 1);
                     mbar_wait(&bars->b_full[bs], bph);
                     tc_fence_after();
                     const int chans = min(64, p.Ce - kb * 64);
                     const int k16 = (chans + 15) >> 4;
                     const uint32_t b_base = smem_u32(sB + bs * FP_B_BYTES);
                     for (int mt = 0; mt < 2; ++mt) {
-                        const uint32_t a_base = smem_u32(sA + (kbuf * 2 + mt) * FP_A_TILE);
+                        const uint32_t a_base = smem_u32(sA + mt * FP_A_TILE);
                         for (int k = 0; k < k16; ++k)
                             tc_mma_f16(tmem_base + mt * p.n_tile, umma_desc_sw128(a_base + k * 32),
                                        umma_desc_sw128(b_base + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(&bars->a_empty[kbuf]);
+                    tc_commit(&bars->a_empty);
                     tc_commit(&bars->b_empty[bs]);
                     if (++bs == FP_NB) { bs = 0; bph ^= 1; }
                 }
@@ -144,98 +148,104 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int cp = threadIdx.x & 15;
         const int sub = (threadIdx.x >> 4) & 1;
         const bool mir = sub != 0;
-        const int blk = (warp << 1) | sub;                 // 16 micro-blocks: 4 x 4 of 4x4 pixels
+        const int grp = warp >> 3;                         // 0: even slabs (channels 0-31 of a K block), 1: odd slabs
+        const int gw = warp & 7;
+        const int blk = (gw << 1) | sub;                   // 16 micro-blocks: 4 x 4 of 4x4 pixels
         const int by = blk >> 2, bx = blk & 3;
         const int oy = by * 4, ox = bx * 4;
         const int cstep = mir ? -(FP_CB / 2) : (FP_CB / 2);
-        uint32_t is = 0, iph = 0, kbc = 0;
+        uint32_t iu = 0, kbc = 0;                          // slabs consumed by this group, K blocks finished
         int it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
-            for (int s = 0; s < p.nslabs; ++s) {
-                const int ch = s * FP_CB + 2 * cp;
-                const bool ch_ok = ch < p.Ce;
-                // weights of this slab for my channel pair (tap-major [49][Ce]); mirrored lanes read kx reversed
-                __half2 wreg[K * K];
-                {
-                    const __half* wb = p.w_dw + ch + (mir ? (K - 1) * p.Ce : 0);
-                    const int wstep = mir ? -p.Ce : p.Ce;
-#pragma unroll
-                    for (int ky = 0; ky < K; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < K; ++kx)
-                            wreg[ky * K + kx] = ch_ok ? *reinterpret_cast<const __half2*>(wb + ky * K * p.Ce + kx * wstep)
-                                                      : __floats2half2_rn(0.f, 0.f);
-                }
-                float2 b2 = make_float2(0.f, 0.f);
-                if (ch_ok && p.b_dw) b2 = make_float2(p.b_dw[ch], p.b_dw[ch + 1]);
+            for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
+                const int s = 2 * kb + grp;
+                const bool have = s < p.nslabs;            // the last K block may hold a single slab
                 float2 acc[4][4];
+                if (have) {
+                    const int ch = s * FP_CB + 2 * cp;
+                    const bool ch_ok = ch < p.Ce;
+                    // weights of this slab for my channel pair (tap-major [49][Ce]); mirrored lanes read kx reversed
+                    __half2 wreg[K * K];
+                    {
+                        const __half* wb = p.w_dw + ch + (mir ? (K - 1) * p.Ce : 0);
+                        const int wstep = mir ? -p.Ce : p.Ce;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                        for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = b2;
+                            for (int kx = 0; kx < K; ++kx)
+                                wreg[ky * K + kx] = ch_ok ? *reinterpret_cast<const __half2*>(wb + ky * K * p.Ce + kx * wstep)
+                                                          : __floats2half2_rn(0.f, 0.f);
+                    }
+                    float2 b2 = make_float2(0.f, 0.f);
+                    if (ch_ok && p.b_dw) b2 = make_float2(p.b_dw[ch], p.b_dw[ch + 1]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = b2;
 
-                mbar_wait(&bars->in_full[is], iph);
-                const __half2* tile_in = reinterpret_cast<const __half2*>(sIn + is * FP_IN_STRIDE);
-                const __half2* base = tile_in + (oy * FP_I + ox + (mir ? 9 : 0)) * (FP_CB / 2) + cp;
+                    const uint32_t is = 2 * (iu & 1) + grp;          // this group's stages: grp, grp+2
+                    mbar_wait(&bars->in_full[is], (iu >> 1) & 1);
+                    const __half2* tile_in = reinterpret_cast<const __half2*>(sIn + is * FP_IN_STRIDE);
+                    const __half2* base = tile_in + (oy * FP_I + ox + (mir ? 9 : 0)) * (FP_CB / 2) + cp;
 #pragma unroll
-                for (int r = 0; r < 10; ++r) {
-                    __half2 in[10];
+                    for (int r = 0; r < 10; ++r) {
+                        __half2 in[10];
 #pragma unroll
-                    for (int c = 0; c < 10; ++c) in[c] = base[r * FP_I * (FP_CB / 2) + c * cstep];
+                        for (int c = 0; c < 10; ++c) in[c] = base[r * FP_I * (FP_CB / 2) + c * cstep];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int ky = r - i;
-                        if (ky >= 0 && ky < K) {
+                        for (int i = 0; i < 4; ++i) {
+                            const int ky = r - i;
+                            if (ky >= 0 && ky < K) {
 #pragma unroll
-                            for (int kx = 0; kx < K; ++kx) {
-                                const __half2 wv = wreg[ky * K + kx];
+                                for (int kx = 0; kx < K; ++kx) {
+                                    const __half2 wv = wreg[ky * K + kx];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    acc[i][j].x = fp_fhfma(fp_lo(in[j + kx]), fp_lo(wv), acc[i][j].x);
-                                    acc[i][j].y = fp_fhfma(fp_hi(in[j + kx]), fp_hi(wv), acc[i][j].y);
+                                    for (int j = 0; j < 4; ++j) {
+                                        acc[i][j].x = fp_fhfma(fp_lo(in[j + kx]), fp_lo(wv), acc[i][j].x);
+                                        acc[i][j].y = fp_fhfma(fp_hi(in[j + kx]), fp_hi(wv), acc[i][j].y);
+                                    }
                                 }
                             }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->in_empty[is]);
+                    ++iu;
+                }
+                // the single A buffer is free once the MMAs of the previous K block have retired (long ago in practice)
+                mbar_wait(&bars->a_empty, (kbc & 1) ^ 1);
+                if (have) {
+                    // ReLU6, fp16, into the swizzled A tile: row = pixel, 16-byte chunk j = channels 8j..8j+7 of the K block
+                    uint8_t* a_mt = sA + (by >> 1) * FP_A_TILE;
+                    const int jch = (grp << 2) | (cp >> 2);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int r = ((oy + i) & 7) * 16 + ox + (mir ? 3 - j : j);     // row inside the M-tile
+                            const __half2 v = __floats2half2_rn(fminf(fmaxf(acc[i][j].x, 0.f), 6.f),
+                                                                fminf(fmaxf(acc[i][j].y, 0.f), 6.f));
+                            *reinterpret_cast<__half2*>(a_mt + r * 128 + ((jch ^ (r & 7)) << 4) + ((cp & 3) << 2)) = v;
+                        }
+                    fence_proxy_async();
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->in_empty[is]);
-                if (++is == FP_NIN) { is = 0; iph ^= 1; }
-
-                // ReLU6, fp16, into the swizzled A tile: row = pixel, 16-byte chunk j holds channels 8j..8j+7 of the K block
-                const uint32_t kbuf = kbc & 1;
-                if ((s & 1) == 0) mbar_wait(&bars->a_empty[kbuf], ((kbc >> 1) & 1) ^ 1);
-                uint8_t* a_mt = sA + (kbuf * 2 + (by >> 1)) * FP_A_TILE;
-                const int jch = ((s & 1) << 2) | (cp >> 2);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = ((oy + i) & 7) * 16 + ox + (mir ? 3 - j : j);     // row inside the M-tile
-                        const __half2 v = __floats2half2_rn(fminf(fmaxf(acc[i][j].x, 0.f), 6.f),
-                                                            fminf(fmaxf(acc[i][j].y, 0.f), 6.f));
-                        *reinterpret_cast<__half2*>(a_mt + r * 128 + ((jch ^ (r & 7)) << 4) + ((cp & 3) << 2)) = v;
-                    }
-                if ((s & 1) || s == p.nslabs - 1) {
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->a_full[kbuf]);
-                    ++kbc;
-                }
+                if (lane == 0) mbar_arrive(&bars->a_full);
             }
             // ---- epilogue: accumulator row = pixel (mt = warp>>2, row = (warp&3)*32 + lane)
             mbar_wait(&bars->tmem_full, it & 1);
             tc_fence_after();
             {
-                const int mt = warp >> 2, row = (warp & 3) * 32 + lane;
+                const int mt = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+                const int chalf = warp >> 3;               // the two groups take alternate 16-column chunks
                 const int py = mt * 8 + (row >> 4), px = row & 15;
                 const int gy = ty * FP_T + py, gx = tx * FP_T + px;
                 const bool valid = gy < p.H && gx < p.W;
                 const size_t off = (((size_t)n * p.H + gy) * p.W + gx) * p.Co;
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + mt * p.n_tile;
                 uint32_t r[16];
-                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                for (int c0 = chalf * 16; c0 < p.n_tile; c0 += 32) {
                     tc_ld16(taddr + c0, r);
                     tc_wait_ld();
                     if (valid && c0 < p.Co) {
@@ -286,7 +296,7 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == FP_DW_WARPS + 1) {
         tc_fence_after();
         tc_dealloc(tmem_base, 512);
     }
