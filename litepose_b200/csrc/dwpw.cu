@@ -21,7 +21,9 @@ constexpr int FP_T = 16;                         // output tile side
 constexpr int FP_I = FP_T + 6;                   // haloed input side (k = 7)
 constexpr int FP_CB = 32;                        // channels per slab
 constexpr int FP_IN_BYTES = FP_I * FP_I * FP_CB * 2;          // 30976
-constexpr int FP_IN_STRIDE = 31744;                           // ring pitch (multiple of 1024)
+constexpr int FP_W_BYTES = 49 * FP_CB * 2;                     // depthwise weights of one slab, 3136 B
+constexpr int FP_IN_STRIDE = 34816;                           // ring pitch: input tile + weight slab (multiple of 1024)
+constexpr int FP_W_OFF = 31744;                               // weights inside a ring stage (128-byte aligned)
 constexpr int FP_NIN = 4;                                      // slab ring: even slabs use stages 0/2, odd 1/3
 constexpr int FP_A_TILE = 128 * 64 * 2;                       // one M-tile x one 64-channel K block, 16 KiB
 constexpr int FP_NB = 2;
@@ -59,7 +61,7 @@ __device__ __forceinline__ unsigned short fp_hi(__half2 v) { return __half_as_us
 
 __global__ void __launch_bounds__(FP_THREADS, 1)
 dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                   const __grid_constant__ FpParams p) {
+                   const __grid_constant__ CUtensorMap map_dw, const __grid_constant__ FpParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sIn = smem;                                         // FP_NIN x [22][22][32] fp16
     uint8_t* sA = smem + FP_NIN * FP_IN_STRIDE;                  // [mtile 2] x 16 KiB, 128B-swizzled
@@ -73,6 +75,7 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_dw);
         for (int i = 0; i < FP_NIN; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 8); }
         mbar_init(&bars->a_full, FP_DW_WARPS);
         mbar_init(&bars->a_empty, 1);
@@ -107,9 +110,10 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const int g = s & 1;                              // even / odd slab group, stages g and g+2
                     const uint32_t is = 2 * (iu[g] & 1) + g;
                     mbar_wait(&bars->in_empty[is], ((iu[g] >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&bars->in_full[is], FP_IN_BYTES);
+                    mbar_expect_tx(&bars->in_full[is], FP_IN_BYTES + FP_W_BYTES);
                     tma_load_4d(sIn + is * FP_IN_STRIDE, &map_x, &bars->in_full[is], s * FP_CB, tx * FP_T - 3,
                                 ty * FP_T - 3, n);
+                    tma_load_2d(sIn + is * FP_IN_STRIDE + FP_W_OFF, &map_dw, &bars->in_full[is], s * FP_CB, 0);
                     ++iu[g];
                 }
             }
@@ -165,18 +169,6 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (have) {
                     const int ch = s * FP_CB + 2 * cp;
                     const bool ch_ok = ch < p.Ce;
-                    // weights of this slab for my channel pair (tap-major [49][Ce]); mirrored lanes read kx reversed
-                    __half2 wreg[K * K];
-                    {
-                        const __half* wb = p.w_dw + ch + (mir ? (K - 1) * p.Ce : 0);
-                        const int wstep = mir ? -p.Ce : p.Ce;
-#pragma unroll
-                        for (int ky = 0; ky < K; ++ky)
-#pragma unroll
-                            for (int kx = 0; kx < K; ++kx)
-                                wreg[ky * K + kx] = ch_ok ? *reinterpret_cast<const __half2*>(wb + ky * K * p.Ce + kx * wstep)
-                                                          : __floats2half2_rn(0.f, 0.f);
-                    }
                     float2 b2 = make_float2(0.f, 0.f);
                     if (ch_ok && p.b_dw) b2 = make_float2(p.b_dw[ch], p.b_dw[ch + 1]);
 #pragma unroll
@@ -186,6 +178,18 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
                     const uint32_t is = 2 * (iu & 1) + grp;          // this group's stages: grp, grp+2
                     mbar_wait(&bars->in_full[is], (iu >> 1) & 1);
+                    // weights of this slab (TMA-staged next to the input tile, [49][32] fp16; channels beyond Ce are
+                    // zero-filled by the tensor map); mirrored lanes read kx reversed
+                    __half2 wreg[K * K];
+                    {
+                        const __half2* ws = reinterpret_cast<const __half2*>(sIn + is * FP_IN_STRIDE + FP_W_OFF) + cp +
+                                            (mir ? (K - 1) * (FP_CB / 2) : 0);
+                        const int wstep = mir ? -(FP_CB / 2) : (FP_CB / 2);
+#pragma unroll
+                        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < K; ++kx) wreg[ky * K + kx] = ws[ky * K * (FP_CB / 2) + kx * wstep];
+                    }
                     const __half2* tile_in = reinterpret_cast<const __half2*>(sIn + is * FP_IN_STRIDE);
                     const __half2* base = tile_in + (oy * FP_I + ox + (mir ? 9 : 0)) * (FP_CB / 2) + cp;
 #pragma unroll
@@ -316,7 +320,7 @@ extern "C" int lp_dw7_project_f16(const void* x, const void* w_dw, const float* 
     LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && Ce >= 8 && Ce % 8 == 0 && Co >= 8 && Co % 8 == 0 && Co <= 160,
                  "lp_dw7_project_f16: bad shape N=%d H=%d W=%d Ce=%d Co=%d (Co <= 160)", N, H, W, Ce, Co);
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w_proj_packed) |
-         reinterpret_cast<uintptr_t>(residual)) & 15) {
+         reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(w_dw)) & 15) {
         set_error("lp_dw7_project_f16: pointers must be 16-byte aligned");
         return LP_ERR_ALIGN;
     }
@@ -348,11 +352,19 @@ extern "C" int lp_dw7_project_f16(const void* x, const void* w_dw, const float* 
         rc = make_tmap(&mw, w_proj_packed, 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
+    CUtensorMap md;
+    {
+        uint64_t d2[2] = {(uint64_t)Ce, 49u};
+        uint64_t s2[1] = {(uint64_t)Ce * 2};
+        uint32_t b2[2] = {(uint32_t)FP_CB, 49u};
+        int rc = make_tmap(&md, w_dw, 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
     cudaError_t e = cudaFuncSetAttribute((const void*)dw7_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FP_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw7_project)");
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    dw7_project_kernel<<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(mx, mw, p);
+    dw7_project_kernel<<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(mx, mw, md, p);
     LP_LAUNCH_CHECK("dw7_project_kernel");
     return LP_OK;
 }
