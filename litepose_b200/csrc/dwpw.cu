@@ -22,7 +22,7 @@ constexpr int FP_I = FP_T + 6;                   // haloed input side (k = 7)
 constexpr int FP_CB = 32;                        // channels per slab
 constexpr int FP_IN_BYTES = FP_I * FP_I * FP_CB * 2;          // 30976
 constexpr int FP_W_BYTES = 49 * FP_CB * 2;                     // depthwise weights of one slab, 3136 B
-constexpr int FP_IN_STRIDE = 34816;                           // ring pitch: input tile + weight slab (multiple of 1024)
+constexpr int FP_IN_STRIDE = 35840;                           // ring pitch: input tile + weight slab (multiple of 1024)
 constexpr int FP_W_OFF = 31744;                               // weights inside a ring stage (128-byte aligned)
 constexpr int FP_NIN = 4;                                      // slab ring: even slabs use stages 0/2, odd 1/3
 constexpr int FP_A_TILE = 128 * 64 * 2;                       // one M-tile x one 64-channel K block, 16 KiB
@@ -30,6 +30,7 @@ constexpr int FP_NB = 2;
 constexpr int FP_B_BYTES = 160 * 64 * 2;                      // Co <= 160
 constexpr int FP_DW_WARPS = 16;                                // two groups of 8: even / odd 32-channel slabs
 constexpr int FP_THREADS = (FP_DW_WARPS + 2) * 32;
+static_assert(FP_W_OFF >= FP_IN_BYTES && FP_W_OFF + FP_W_BYTES <= FP_IN_STRIDE, "ring stage layout");
 constexpr size_t FP_SMEM = (size_t)FP_NIN * FP_IN_STRIDE + 2 * FP_A_TILE + FP_NB * FP_B_BYTES + 1024 + 1024;
 
 struct FpBars {
