@@ -31,7 +31,8 @@ constexpr int FP_B_BYTES = 160 * 64 * 2;                      // Co <= 160
 constexpr int FP_DW_WARPS = 16;                                // two groups of 8: even / odd 32-channel slabs
 constexpr int FP_THREADS = (FP_DW_WARPS + 2) * 32;
 static_assert(FP_W_OFF >= FP_IN_BYTES && FP_W_OFF + FP_W_BYTES <= FP_IN_STRIDE, "ring stage layout");
-constexpr size_t FP_SMEM = (size_t)FP_NIN * FP_IN_STRIDE + 2 * FP_A_TILE + FP_NB * FP_B_BYTES + 1024 + 1024;
+constexpr int FP_MAX_CE = 1024;
+constexpr size_t FP_SMEM = (size_t)FP_NIN * FP_IN_STRIDE + 2 * FP_A_TILE + FP_NB * FP_B_BYTES + 1024 + FP_MAX_CE * 4 + 1024;
 
 struct FpBars {
     uint64_t in_full[FP_NIN], in_empty[FP_NIN];
@@ -67,8 +68,9 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     uint8_t* sIn = smem;                                         // FP_NIN x [22][22][32] fp16
     uint8_t* sA = smem + FP_NIN * FP_IN_STRIDE;                  // [mtile 2] x 16 KiB, 128B-swizzled
     uint8_t* sB = sA + 2 * FP_A_TILE;                            // FP_NB x [n_tile][64] fp16, 128B-swizzled
-    float* sBias = reinterpret_cast<float*>(sB + FP_NB * FP_B_BYTES);
-    FpBars* bars = reinterpret_cast<FpBars*>(sBias + 192);
+    float* sBias = reinterpret_cast<float*>(sB + FP_NB * FP_B_BYTES);    // projection bias (<= 160)
+    float* sBdw = sBias + 192;                                            // depthwise bias (<= FP_MAX_CE)
+    FpBars* bars = reinterpret_cast<FpBars*>(sBdw + FP_MAX_CE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int K = 7;
@@ -90,6 +92,7 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc_relinquish();
     }
     for (int i = threadIdx.x; i < p.n_tile; i += FP_THREADS) sBias[i] = p.b_pj ? p.b_pj[i] : 0.f;
+    for (int i = threadIdx.x; i < p.nslabs * FP_CB; i += FP_THREADS) sBdw[i] = (p.b_dw && i < p.Ce) ? p.b_dw[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -169,9 +172,7 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 float2 acc[4][4];
                 if (have) {
                     const int ch = s * FP_CB + 2 * cp;
-                    const bool ch_ok = ch < p.Ce;
-                    float2 b2 = make_float2(0.f, 0.f);
-                    if (ch_ok && p.b_dw) b2 = make_float2(p.b_dw[ch], p.b_dw[ch + 1]);
+                    const float2 b2 = *reinterpret_cast<const float2*>(sBdw + ch);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -318,8 +319,9 @@ extern "C" int lp_dw7_project_f16(const void* x, const void* w_dw, const float* 
                                   const float* b_proj_packed, const void* residual, void* out, int N, int H, int W,
                                   int Ce, int Co, lp_stream_t stream) {
     LP_CHECK_ARG(x && w_dw && w_proj_packed && out, "lp_dw7_project_f16: null pointer");
-    LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && Ce >= 8 && Ce % 8 == 0 && Co >= 8 && Co % 8 == 0 && Co <= 160,
-                 "lp_dw7_project_f16: bad shape N=%d H=%d W=%d Ce=%d Co=%d (Co <= 160)", N, H, W, Ce, Co);
+    LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && Ce >= 8 && Ce % 8 == 0 && Ce <= FP_MAX_CE - FP_CB && Co >= 8 && Co % 8 == 0 &&
+                     Co <= 160,
+                 "lp_dw7_project_f16: bad shape N=%d H=%d W=%d Ce=%d Co=%d (Ce <= 992, Co <= 160)", N, H, W, Ce, Co);
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w_proj_packed) |
          reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(w_dw)) & 15) {
         set_error("lp_dw7_project_f16: pointers must be 16-byte aligned");

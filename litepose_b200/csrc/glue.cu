@@ -168,6 +168,124 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
     }
 }
 
+// ---- exact 4x path (the evaluation config: flip test + PROJECT2IMAGE to 4h x 4w) -------------------------------
+// One thread produces a 4x4 output block of one (n, j) plane for all four maps entirely in registers: 3x3
+// neighbourhoods of the quarter-resolution maps + 4x4 neighbourhoods of the half-resolution maps, both x2 bilinear
+// stages with their constant weights (edge clamping == clamping the source index), flip = mirrored block with
+// reversed columns.  No shared memory, no barriers; 16-byte stores.
+__device__ __forceinline__ void up4(const float a, const float b, const float c, float (&o)[4]) {
+    // mid rows/cols (2i-1, 2i, 2i+1, 2i+2) of a x2 up-sample from neighbours (i-1, i, i+1)
+    o[0] = 0.75f * a + 0.25f * b;
+    o[1] = 0.25f * a + 0.75f * b;
+    o[2] = 0.75f * b + 0.25f * c;
+    o[3] = 0.25f * b + 0.75f * c;
+}
+__device__ __forceinline__ void proj4(const float (&m)[4], float (&o)[4]) {
+    // outputs (4i .. 4i+3) from mid samples (2i-1 .. 2i+2)
+    o[0] = 0.25f * m[0] + 0.75f * m[1];
+    o[1] = 0.75f * m[1] + 0.25f * m[2];
+    o[2] = 0.25f * m[1] + 0.75f * m[2];
+    o[3] = 0.75f * m[2] + 0.25f * m[3];
+}
+
+// mid[4][4] = U(q)[rows 2a-1..2a+2][cols 2b-1..2b+2]   (q: quarter-resolution plane, clamped 3x3 neighbourhood)
+__device__ __forceinline__ void mid_from_quarter(const float* __restrict__ q, int w, int ra, int rb, int rc, int ca, int cb,
+                                                 int cc, float (&mid)[4][4]) {
+    float r[3][4];
+    const int rows[3] = {ra, rb, rc};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) up4(__ldg(q + rows[i] * w + ca), __ldg(q + rows[i] * w + cb), __ldg(q + rows[i] * w + cc), r[i]);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        float col[4];
+        up4(r[0][x], r[1][x], r[2][x], col);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) mid[y][x] = col[y];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+glue_x4_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const float* __restrict__ f0,
+               const float* __restrict__ f1, const int32_t* __restrict__ flip_index, int J, int h, int w,
+               float* __restrict__ det, float* __restrict__ tag) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;     // quarter-resolution column
+    const int a = blockIdx.y;                                // quarter-resolution row
+    const int n = blockIdx.z / J, j = blockIdx.z - n * J;
+    if (b >= w) return;
+    const int H2 = 2 * h, W2 = 2 * w, Hd = 4 * h, Wd = 4 * w;
+    const size_t hw = (size_t)h * w, HW2 = (size_t)H2 * W2;
+    const int fj = flip_index[j];
+    const int ra = max(a - 1, 0), rc = min(a + 1, h - 1);
+    const int bf = w - 1 - b;                                // mirrored block of the flipped pass
+    float ha[4][4], hf[4][4], t0[4][4], t1[4][4], tmp[4][4];
+
+    // plain pass
+    mid_from_quarter(o0 + ((size_t)n * 2 * J + j) * hw, w, ra, a, rc, max(b - 1, 0), b, min(b + 1, w - 1), ha);
+    mid_from_quarter(o0 + ((size_t)n * 2 * J + J + j) * hw, w, ra, a, rc, max(b - 1, 0), b, min(b + 1, w - 1), t0);
+    {
+        const float* p1 = o1 + ((size_t)n * J + j) * HW2;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int yy = min(max(2 * a - 1 + y, 0), H2 - 1);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int xx = min(max(2 * b - 1 + x, 0), W2 - 1);
+                ha[y][x] = (ha[y][x] + __ldg(p1 + (size_t)yy * W2 + xx)) / 2.f;
+            }
+        }
+    }
+    // flipped pass: same block pattern at the mirrored column block, columns reversed, channels permuted
+    mid_from_quarter(f0 + ((size_t)n * 2 * J + fj) * hw, w, ra, a, rc, max(bf - 1, 0), bf, min(bf + 1, w - 1), tmp);
+    {
+        const float* p1 = f1 + ((size_t)n * J + fj) * HW2;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int yy = min(max(2 * a - 1 + y, 0), H2 - 1);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int xx = min(max(2 * bf - 1 + x, 0), W2 - 1);
+                hf[y][3 - x] = (tmp[y][x] + __ldg(p1 + (size_t)yy * W2 + xx)) / 2.f;
+            }
+        }
+    }
+    mid_from_quarter(f0 + ((size_t)n * 2 * J + J + fj) * hw, w, ra, a, rc, max(bf - 1, 0), bf, min(bf + 1, w - 1), tmp);
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) t1[y][3 - x] = tmp[y][x];
+
+    // projection x2 (rows then columns) and aggregation
+    float od[4][4], ot0[4][4], ot1[4][4];
+#define GL_PROJ(SRC, DST)                                                 \
+    {                                                                     \
+        float v[4][4];                                                    \
+        _Pragma("unroll") for (int x = 0; x < 4; ++x) {                   \
+            const float m[4] = {SRC[0][x], SRC[1][x], SRC[2][x], SRC[3][x]}; \
+            float o[4];                                                   \
+            proj4(m, o);                                                  \
+            _Pragma("unroll") for (int y = 0; y < 4; ++y) v[y][x] = o[y]; \
+        }                                                                 \
+        _Pragma("unroll") for (int y = 0; y < 4; ++y) proj4(v[y], DST[y]); \
+    }
+    float pa[4][4], pf[4][4];
+    GL_PROJ(ha, pa) GL_PROJ(hf, pf) GL_PROJ(t0, ot0) GL_PROJ(t1, ot1)
+#undef GL_PROJ
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) od[y][x] = (pa[y][x] + pf[y][x]) / 2.f;
+
+    float* dplane = det + ((size_t)n * J + j) * Hd * Wd;
+    float* tplane = tag + ((size_t)n * J + j) * Hd * Wd * 2;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        const size_t o = (size_t)(4 * a + y) * Wd + 4 * b;
+        *reinterpret_cast<float4*>(dplane + o) = make_float4(od[y][0], od[y][1], od[y][2], od[y][3]);
+        *reinterpret_cast<float4*>(tplane + o * 2) = make_float4(ot0[y][0], ot1[y][0], ot0[y][1], ot1[y][1]);
+        *reinterpret_cast<float4*>(tplane + o * 2 + 4) = make_float4(ot0[y][2], ot1[y][2], ot0[y][3], ot1[y][3]);
+    }
+}
+
 }  // namespace lp
 
 using namespace lp;
@@ -188,6 +306,12 @@ extern "C" int lp_glue_f32(const float* o0, const float* o1, const float* f0, co
     if (((reinterpret_cast<uintptr_t>(tag) & 15) || (reinterpret_cast<uintptr_t>(det) & 7)) && flip) {
         set_error("lp_glue_f32: tag must be 16-byte and det 8-byte aligned");
         return LP_ERR_ALIGN;
+    }
+    if (flip && Hd == 4 * h && Wd == 4 * w && (long long)N * J <= 65535 && h <= 65535) {
+        dim3 grid((w + 127) / 128, h, N * J);
+        glue_x4_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(o0, o1, f0, f1, flip_index, J, h, w, det, tag);
+        LP_LAUNCH_CHECK("glue_x4_kernel");
+        return LP_OK;
     }
     const int tiles_x = (Wd + GL_TO - 1) / GL_TO, tiles_y = (Hd + GL_TO - 1) / GL_TO;
     dim3 grid(tiles_x * tiles_y, J, N);

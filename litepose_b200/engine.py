@@ -178,7 +178,7 @@ class LitePoseEngine(object):
                                                       _lib.ACT_RELU6]))
             out = buf(n, oh, ow, pc["N"])
             keep.append(out)
-            if self.fuse_dw_project and blk["stride"] == 1 and dw["k"] == 7 and pc["N"] <= 160:
+            if self.fuse_dw_project and blk["stride"] == 1 and dw["k"] == 7 and pc["N"] <= 160 and dw["C"] <= 992:
                 # depthwise + projection (+ identity) in one kernel: the expanded dw output never reaches HBM
                 ops.append(_Op("dw7_project", lib.lp_dw7_project_f16,
                                [e_buf.data_ptr(), dw["w"].data_ptr(), dw["b"].data_ptr(), pc["w"].data_ptr(),
