@@ -14,7 +14,11 @@ namespace lp {
 constexpr int ST_TW = 64, ST_TH = 8;                          // output tile; each thread owns 2 x-adjacent pixels
 constexpr int ST_IH = ST_TH * 2 + 1;                          // 17 input rows (stride 2, pad 1)
 constexpr int ST_IW = ST_TW * 2 + 1;                          // 129 input columns actually used
-template <typename TIn> struct StBox { static constexpr int W = (sizeof(TIn) == 2) ? 136 : 132; };   // 16-byte multiple
+// the patch is fetched as NB column chunks of 128 bytes (TMA boxes with a wider inner extent faulted on B200)
+template <typename TIn> struct StBox {
+    static constexpr int W = 128 / sizeof(TIn);                  // columns per chunk: 64 (fp16) / 32 (fp32)
+    static constexpr int NB = (ST_IW + W - 1) / W;               // 3 / 5 chunks
+};
 
 // The 3-plane haloed input patch arrives with ONE TMA tensor copy (OOB zero fill = conv padding; the box of the flip
 // pass is taken from the mirrored column range and read backwards), so the load is a single asynchronous transaction
@@ -23,8 +27,8 @@ template <typename TIn>
 __global__ void __launch_bounds__(256)
 stem_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict__ w, const float* __restrict__ bias,
             __half* __restrict__ y, int H, int W, int flip_x) {
-    constexpr int BW = StBox<TIn>::W;
-    __shared__ __align__(128) TIn s_in[3][ST_IH][BW];
+    constexpr int BW = StBox<TIn>::W, NB = StBox<TIn>::NB;
+    __shared__ __align__(128) TIn s_in[NB][3][ST_IH][BW];
     __shared__ __align__(16) float s_w[27][32];   // [tap][co]
     __shared__ __align__(16) float s_b[32];
     __shared__ __align__(8) uint64_t bar;
@@ -36,14 +40,15 @@ stem_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict_
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
-        mbar_expect_tx(&bar, 3 * ST_IH * BW * (int)sizeof(TIn));
-        // tile-local column c lives at smem column c (plain) or ST_IW-1-c (flip: box starts at the mirror of ix0+128)
+        mbar_expect_tx(&bar, NB * 3 * ST_IH * BW * (int)sizeof(TIn));
+        // tile-local column c lives at patch column c (plain) or ST_IW-1-c (flip: box starts at the mirror of ix0+128)
         const int xs = flip_x ? (W - ST_IW - ix0) : ix0;
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-            ::"r"(smem_u32(&s_in[0][0][0])), "l"(reinterpret_cast<uint64_t>(&map_x)), "r"(smem_u32(&bar)), "r"(xs),
-            "r"(iy0), "r"(n * 3)
-            : "memory");
+        for (int b = 0; b < NB; ++b)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(&s_in[b][0][0][0])), "l"(reinterpret_cast<uint64_t>(&map_x)), "r"(smem_u32(&bar)),
+                "r"(xs + b * BW), "r"(iy0), "r"(n * 3)
+                : "memory");
     }
     for (int i = threadIdx.x; i < 27 * 32; i += 256) {
         const int co = i & 31, t = i >> 5;
@@ -64,10 +69,12 @@ stem_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict_
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             // the two pixels need input columns 4*lx .. 4*lx+4
-            const TIn* row = &s_in[c][2 * ly + ky][cbase];
             float v[5];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) v[q] = (float)row[q * cstep];
+            for (int q = 0; q < 5; ++q) {
+                const int col = cbase + q * cstep;
+                v[q] = (float)s_in[col / BW][c][2 * ly + ky][col % BW];
+            }
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const float4* wr = reinterpret_cast<const float4*>(s_w[c * 9 + ky * 3 + kx]);
