@@ -44,11 +44,7 @@ stem_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict_
         // tile-local column c lives at patch column c (plain) or ST_IW-1-c (flip: box starts at the mirror of ix0+128)
         const int xs = flip_x ? (W - ST_IW - ix0) : ix0;
         for (int b = 0; b < NB; ++b)
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                ::"r"(smem_u32(&s_in[b][0][0][0])), "l"(reinterpret_cast<uint64_t>(&map_x)), "r"(smem_u32(&bar)),
-                "r"(xs + b * BW), "r"(iy0), "r"(n * 3)
-                : "memory");
+            tma_load_4d(&s_in[b][0][0][0], &map_x, &bar, xs + b * BW, iy0, 0, n);
     }
     for (int i = threadIdx.x; i < 27 * 32; i += 256) {
         const int co = i & 31, t = i >> 5;
@@ -118,10 +114,10 @@ template <typename TIn>
 static int launch_stem(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int flip_x,
                        cudaStream_t stream) {
     CUtensorMap map;
-    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)N * 3};
-    uint64_t strides[2] = {(uint64_t)W * sizeof(TIn), (uint64_t)H * W * sizeof(TIn)};
-    uint32_t box[3] = {(uint32_t)StBox<TIn>::W, (uint32_t)ST_IH, 3u};
-    int rc = make_tmap(&map, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+    uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, 3u, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)W * sizeof(TIn), (uint64_t)H * W * sizeof(TIn), (uint64_t)3 * H * W * sizeof(TIn)};
+    uint32_t box[4] = {(uint32_t)StBox<TIn>::W, (uint32_t)ST_IH, 3u, 1u};
+    int rc = make_tmap(&map, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
                        sizeof(TIn) == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     if (rc) return rc;
     dim3 grid((W / 2 + ST_TW - 1) / ST_TW, (H / 2 + ST_TH - 1) / ST_TH, N);
