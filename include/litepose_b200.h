@@ -67,7 +67,7 @@ void lp_reset_launch_count(void);
 
 /* ---- M1: stem conv3x3 stride 2 (3 -> 32) + bias + ReLU6 ------------------
  * x: NCHW [N,3,H,W], fp32 (x_is_fp32 != 0) or fp16;  w: fp16 [32][27] (co, ci*9+ky*3+kx)
- * BN-folded;  bias: fp32 [32];  y: NHWC fp16 [N,H/2,W/2,32].  H even, W % 8 == 0 (TMA row pitch).
+ * BN-folded;  bias: fp32 [32];  y: NHWC fp16 [N,H/2,W/2,32].  H, W even.
  * flip_x != 0 reads the image mirrored along W, i.e. computes the stem of
  * torch.flip(x, [3]) (the flip-test pass, lib/core/inference.py:120) without a copy. */
 int lp_stem_conv3x3_s2(const void* x, int x_is_fp32, int flip_x, const void* w, const float* bias,

@@ -12,79 +12,86 @@
 namespace lp {
 
 constexpr int ST_TW = 64, ST_TH = 8;                          // output tile; each thread owns 2 x-adjacent pixels
-constexpr int ST_IH = ST_TH * 2 + 1;                          // 17 input rows (stride 2, pad 1)
-constexpr int ST_IW = ST_TW * 2 + 1;                          // 129 input columns actually used
-// the patch is fetched as NB column chunks of 128 bytes (TMA boxes with a wider inner extent faulted on B200)
-template <typename TIn> struct StBox {
-    static constexpr int W = 128 / sizeof(TIn);                  // columns per chunk: 64 (fp16) / 32 (fp32)
-    static constexpr int NB = (ST_IW + W - 1) / W;               // 3 / 5 chunks
-};
+constexpr int ST_IW = ST_TW * 2 + 1, ST_IH = ST_TH * 2 + 1;   // 129 x 17 input patch (stride 2, pad 1)
+constexpr int ST_IWP = ST_IW + 3;                              // row pitch 132 floats
 
-// The 3-plane haloed input patch arrives with ONE TMA tensor copy (OOB zero fill = conv padding; the box of the flip
-// pass is taken from the mirrored column range and read backwards), so the load is a single asynchronous transaction
-// instead of a chain of dependent global loads.
 template <typename TIn>
 __global__ void __launch_bounds__(256)
-stem_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict__ w, const float* __restrict__ bias,
+stem_kernel(const TIn* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
             __half* __restrict__ y, int H, int W, int flip_x) {
-    constexpr int BW = StBox<TIn>::W, NB = StBox<TIn>::NB;
-    __shared__ __align__(128) TIn s_in[NB][3][ST_IH][BW];
+    __shared__ __align__(16) float s_in[3][ST_IH][ST_IWP];
     __shared__ __align__(16) float s_w[27][32];   // [tap][co]
     __shared__ __align__(16) float s_b[32];
-    __shared__ __align__(8) uint64_t bar;
     const int Ho = H / 2, Wo = W / 2;
     const int n = blockIdx.z;
     const int ox0 = blockIdx.x * ST_TW, oy0 = blockIdx.y * ST_TH;
     const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
 
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_barrier_init();
-        mbar_expect_tx(&bar, NB * 3 * ST_IH * BW * (int)sizeof(TIn));
-        // tile-local column c lives at patch column c (plain) or ST_IW-1-c (flip: box starts at the mirror of ix0+128)
-        const int xs = flip_x ? (W - ST_IW - ix0) : ix0;
-        for (int b = 0; b < NB; ++b)
-            tma_load_4d(&s_in[b][0][0][0], &map_x, &bar, xs + b * BW, iy0, 0, n);
-    }
     for (int i = threadIdx.x; i < 27 * 32; i += 256) {
         const int co = i & 31, t = i >> 5;
         s_w[t][co] = __half2float(w[co * 27 + t]);
     }
     if (threadIdx.x < 32) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    const TIn* xn = x + (size_t)n * 3 * H * W;
+    // patch load: 3*17 rows of 129 floats; 8 independent global loads in flight per thread
+    constexpr int NELEM = 3 * ST_IH * ST_IW;
+    for (int i0 = threadIdx.x; i0 < NELEM; i0 += 256 * 8) {
+        float tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            float v = 0.f;
+            if (i < NELEM) {
+                const int c = i / (ST_IH * ST_IW);
+                const int rem = i - c * (ST_IH * ST_IW);
+                const int r = rem / ST_IW, col = rem - r * ST_IW;
+                const int gy = iy0 + r, gx = ix0 + col;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+                    v = (float)xn[((size_t)c * H + gy) * W + (flip_x ? W - 1 - gx : gx)];
+            }
+            tmp[u] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            if (i < NELEM) {
+                const int c = i / (ST_IH * ST_IW);
+                const int rem = i - c * (ST_IH * ST_IW);
+                const int r = rem / ST_IW, col = rem - r * ST_IW;
+                s_in[c][r][col] = tmp[u];
+            }
+        }
+    }
     __syncthreads();
-    mbar_wait(&bar, 0);
 
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;    // pixels (2*lx, 2*lx+1) of row ly
     float acc0[32], acc1[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc0[i] = acc1[i] = s_b[i];
-    const int cbase = flip_x ? (ST_IW - 1 - 4 * lx) : 4 * lx;
-    const int cstep = flip_x ? -1 : 1;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             // the two pixels need input columns 4*lx .. 4*lx+4
-            float v[5];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const int col = cbase + q * cstep;
-                v[q] = (float)s_in[col / BW][c][2 * ly + ky][col % BW];
-            }
+            const float* row = &s_in[c][2 * ly + ky][4 * lx];
+            const float4 a = *reinterpret_cast<const float4*>(row);
+            const float e = row[4];
+            const float in0[3] = {a.x, a.y, a.z};
+            const float in1[3] = {a.z, a.w, e};
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const float4* wr = reinterpret_cast<const float4*>(s_w[c * 9 + ky * 3 + kx]);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     const float4 wv = wr[g];
-                    acc0[4 * g + 0] = fmaf(v[kx], wv.x, acc0[4 * g + 0]);
-                    acc0[4 * g + 1] = fmaf(v[kx], wv.y, acc0[4 * g + 1]);
-                    acc0[4 * g + 2] = fmaf(v[kx], wv.z, acc0[4 * g + 2]);
-                    acc0[4 * g + 3] = fmaf(v[kx], wv.w, acc0[4 * g + 3]);
-                    acc1[4 * g + 0] = fmaf(v[kx + 2], wv.x, acc1[4 * g + 0]);
-                    acc1[4 * g + 1] = fmaf(v[kx + 2], wv.y, acc1[4 * g + 1]);
-                    acc1[4 * g + 2] = fmaf(v[kx + 2], wv.z, acc1[4 * g + 2]);
-                    acc1[4 * g + 3] = fmaf(v[kx + 2], wv.w, acc1[4 * g + 3]);
+                    acc0[4 * g + 0] = fmaf(in0[kx], wv.x, acc0[4 * g + 0]);
+                    acc0[4 * g + 1] = fmaf(in0[kx], wv.y, acc0[4 * g + 1]);
+                    acc0[4 * g + 2] = fmaf(in0[kx], wv.z, acc0[4 * g + 2]);
+                    acc0[4 * g + 3] = fmaf(in0[kx], wv.w, acc0[4 * g + 3]);
+                    acc1[4 * g + 0] = fmaf(in1[kx], wv.x, acc1[4 * g + 0]);
+                    acc1[4 * g + 1] = fmaf(in1[kx], wv.y, acc1[4 * g + 1]);
+                    acc1[4 * g + 2] = fmaf(in1[kx], wv.z, acc1[4 * g + 2]);
+                    acc1[4 * g + 3] = fmaf(in1[kx], wv.w, acc1[4 * g + 3]);
                 }
             }
         }
@@ -110,23 +117,6 @@ stem_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restrict_
     }
 }
 
-template <typename TIn>
-static int launch_stem(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int flip_x,
-                       cudaStream_t stream) {
-    CUtensorMap map;
-    uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, 3u, (uint64_t)N};
-    uint64_t strides[3] = {(uint64_t)W * sizeof(TIn), (uint64_t)H * W * sizeof(TIn), (uint64_t)3 * H * W * sizeof(TIn)};
-    uint32_t box[4] = {(uint32_t)StBox<TIn>::W, (uint32_t)ST_IH, 3u, 1u};
-    int rc = make_tmap(&map, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
-                       sizeof(TIn) == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
-    if (rc) return rc;
-    dim3 grid((W / 2 + ST_TW - 1) / ST_TW, (H / 2 + ST_TH - 1) / ST_TH, N);
-    stem_kernel<TIn><<<grid, 256, 0, stream>>>(map, reinterpret_cast<const __half*>(w), bias, reinterpret_cast<__half*>(y),
-                                               H, W, flip_x);
-    LP_LAUNCH_CHECK("stem_kernel");
-    return LP_OK;
-}
-
 }  // namespace lp
 
 using namespace lp;
@@ -134,12 +124,21 @@ using namespace lp;
 extern "C" int lp_stem_conv3x3_s2(const void* x, int x_is_fp32, int flip_x, const void* w, const float* bias, void* y,
                                   int N, int H, int W, lp_stream_t stream) {
     LP_CHECK_ARG(x && w && y, "lp_stem_conv3x3_s2: null pointer");
-    LP_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 8 == 0,
-                 "lp_stem_conv3x3_s2: bad shape N=%d H=%d W=%d (H even, W %% 8 == 0)", N, H, W);
-    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15) {
-        set_error("lp_stem_conv3x3_s2: x and y must be 16-byte aligned");
+    LP_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
+                 "lp_stem_conv3x3_s2: bad shape N=%d H=%d W=%d (H, W even)", N, H, W);
+    if (reinterpret_cast<uintptr_t>(y) & 15) {
+        set_error("lp_stem_conv3x3_s2: y must be 16-byte aligned");
         return LP_ERR_ALIGN;
     }
-    if (x_is_fp32) return launch_stem<float>(x, w, bias, y, N, H, W, flip_x, (cudaStream_t)stream);
-    return launch_stem<__half>(x, w, bias, y, N, H, W, flip_x, (cudaStream_t)stream);
+    dim3 grid((W / 2 + ST_TW - 1) / ST_TW, (H / 2 + ST_TH - 1) / ST_TH, N);
+    if (x_is_fp32)
+        stem_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(x),
+                                                                  reinterpret_cast<const __half*>(w), bias,
+                                                                  reinterpret_cast<__half*>(y), H, W, flip_x);
+    else
+        stem_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(x),
+                                                                   reinterpret_cast<const __half*>(w), bias,
+                                                                   reinterpret_cast<__half*>(y), H, W, flip_x);
+    LP_LAUNCH_CHECK("stem_kernel");
+    return LP_OK;
 }
