@@ -32,7 +32,6 @@ static inline int strip_rows(int W) {
 }
 
 constexpr int TK_SPB = 4;        // strips walked sequentially by one CTA (a "band")
-constexpr int TK_MAXW = 1024;    // candidates are collected per row: never more than W
 
 // Sorted insert of `key` into the descending list s_top[0..ntop) (capacity K <= 64) by one warp.
 __device__ __forceinline__ int topk_insert(unsigned long long* s_top, int ntop, int K, unsigned long long key, int lane) {
@@ -54,28 +53,31 @@ __device__ __forceinline__ int topk_insert(unsigned long long* s_top, int ntop, 
     return nnew;
 }
 
-constexpr int TK_RB = 4;   // rows evaluated per barrier round (they share one threshold)
+constexpr int TK_WARPS = TK_THREADS / 32;
 
-// partial: [N*J][bands][K] keys (sorted, 0 = empty).  One CTA walks TK_SPB strips of SR rows of one plane and keeps a
-// running top-K.  A pixel can only enter the list if its value reaches the current K-th value, so the k x k window
-// maximum (the NMS test) is evaluated ONLY for those pixels: once the list is full the kernel is a plain streaming
-// pass (one shared-memory read and one compare per pixel) and runs at memory speed.
+// partial: [N*J][bands * TK_WARPS][K] keys (sorted, 0 = empty); plane_thr: [N*J] running lower bound of the plane's
+// K-th key (zero-initialised by the caller).  One CTA walks TK_SPB strips of SR rows of one plane; inside a strip every
+// warp owns the rows r == warp (mod 8) and keeps its OWN sorted top-K list (no block barriers, no serial merge).  A pixel
+// can only matter if its key reaches the best known K-th key -- the maximum over all warps of the CTA (shared memory)
+// and over all CTAs of the plane (global memory) of their local K-th keys, each a valid lower bound of the plane's
+// K-th key -- so the k x k window maximum (the NMS test) is evaluated for a vanishing fraction of pixels and the
+// kernel streams at memory speed.  The per-warp lists are merged by topk_merge_kernel.
 __global__ void __launch_bounds__(TK_THREADS)
 nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*window radius*/, int SR, int K,
-                      unsigned long long* __restrict__ partial) {
+                      unsigned long long* __restrict__ partial, unsigned long long* __restrict__ plane_thr) {
     extern __shared__ __align__(16) float sm[];
     const int plane = blockIdx.y;
     const int band = blockIdx.x, nbands = gridDim.x;
     float* s_val = sm;                             // [SR+2R][W] raw values (out-of-image rows hold -inf)
-    __shared__ unsigned long long s_top[TK_MAXK];
-    __shared__ unsigned long long s_cand[TK_RB * TK_MAXW];
-    __shared__ int s_ncand[2], s_ntop;             // candidate counter double-buffered by round parity
+    __shared__ unsigned long long s_top[TK_WARPS][TK_MAXK];
+    __shared__ unsigned long long s_thr;           // CTA-wide lower bound of the K-th key
     const float* p = det + (size_t)plane * H * W;
     const float NEG_INF = __int_as_float(0xff800000);
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { s_ncand[0] = 0; s_ncand[1] = 0; s_ntop = 0; }
-    if (threadIdx.x < TK_MAXK) s_top[threadIdx.x] = 0ull;
-    int par = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = lane; i < TK_MAXK; i += 32) s_top[warp][i] = 0ull;
+    if (threadIdx.x == 0) s_thr = 0ull;
+    int ntop = 0;
+    unsigned long long* mytop = s_top[warp];
     const bool vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 
     for (int st = 0; st < TK_SPB; ++st) {
@@ -111,18 +113,26 @@ nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*windo
             }
         }
         __syncthreads();
-        for (int r0 = 0; r0 < rows; r0 += TK_RB, par ^= 1) {
-            const int ntop0 = s_ntop;
-            const unsigned long long thr = ntop0 >= K ? s_top[K - 1] : 0ull;
-            const float thr_v = __uint_as_float((unsigned)(thr >> 32));          // 0 while the list is not full
-            const int rend = min(r0 + TK_RB, rows);
-            for (int r = r0; r < rend; ++r)
-                for (int x0 = 0; x0 < W; x0 += TK_THREADS) {
-                    const int x = x0 + threadIdx.x;
+        // refresh the bound with what the other CTAs of this plane have found so far
+        unsigned long long thr = s_thr;
+        {
+            const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(plane_thr + plane);
+            thr = g > thr ? g : thr;
+        }
+        for (int r = warp; r < rows; r += TK_WARPS) {
+            for (int x0 = 0; x0 < W; x0 += 32) {
+                const int x = x0 + lane;
+                const float thr_v = __uint_as_float((unsigned)(thr >> 32));      // 0 while no list is full
+                const float v = x < W ? s_val[(r + R) * W + x] : 0.f;
+                bool cand = v > 0.f && v >= thr_v;
+                if (__any_sync(0xffffffffu, cand)) {
                     unsigned long long key = 0ull;
-                    if (x < W) {
-                        const float v = s_val[(r + R) * W + x];
-                        if (v > 0.f && v >= thr_v) {                              // rare once the list is full
+                    if (cand) {
+                        // cheap reject first: most pixels lose against a direct neighbour
+                        const float* c = s_val + (r + R) * W + x;
+                        const float l = x > 0 ? c[-1] : NEG_INF, rr = x < W - 1 ? c[1] : NEG_INF;
+                        if (R > 0) cand = v >= l && v >= rr && v >= c[-W] && v >= c[W];
+                        if (cand) {
                             float m = NEG_INF;
                             const int xa = max(x - R, 0), xb = min(x + R, W - 1);
                             for (int d = 0; d <= 2 * R; ++d)
@@ -133,32 +143,35 @@ nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*windo
                             }
                         }
                     }
-                    const bool cand = key > thr;
-                    const unsigned bal = __ballot_sync(0xffffffffu, cand);
+                    unsigned bal = __ballot_sync(0xffffffffu, key > thr);
                     if (bal) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&s_ncand[par], __popc(bal));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (cand) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = key;
+                        while (bal) {
+                            const int src = __ffs(bal) - 1;
+                            bal &= bal - 1;
+                            const unsigned long long k2 = __shfl_sync(0xffffffffu, key, src);
+                            ntop = topk_insert(mytop, ntop, K, k2, lane);
+                        }
+                        if (ntop >= K) {
+                            const unsigned long long kth = mytop[K - 1];
+                            if (kth > thr) {
+                                if (lane == 0) atomicMax(&s_thr, kth);
+                                thr = kth;
+                            }
+                        }
                     }
                 }
-            __syncthreads();
-            // block-uniform: this round's counter is not touched again before the next round's barrier (the next round
-            // counts into the other slot), so every thread reads the same value here
-            if (s_ncand[par]) {
-                if (threadIdx.x < 32) {
-                    const int nc = s_ncand[par];
-                    int ntop = s_ntop;
-                    for (int c = 0; c < nc; ++c) ntop = topk_insert(s_top, ntop, K, s_cand[c], lane);
-                    if (lane == 0) { s_ntop = ntop; s_ncand[par] = 0; }
-                }
-                __syncthreads();
+                // pick up the bound published by the other warps
+                const unsigned long long sh = *reinterpret_cast<volatile unsigned long long*>(&s_thr);
+                thr = sh > thr ? sh : thr;
             }
         }
+        // publish this CTA's bound to the plane
+        __syncwarp();
+        if (lane == 0 && thr) atomicMax(plane_thr + plane, thr);
     }
-    __syncthreads();
-    unsigned long long* out = partial + ((size_t)plane * nbands + band) * K;
-    for (int k = threadIdx.x; k < K; k += TK_THREADS) out[k] = k < s_ntop ? s_top[k] : 0ull;
+    __syncwarp();
+    unsigned long long* out = partial + (((size_t)plane * nbands + band) * TK_WARPS + warp) * K;
+    for (int k = lane; k < K; k += 32) out[k] = k < ntop ? mytop[k] : 0ull;
 }
 
 // one warp per plane
@@ -213,7 +226,8 @@ extern "C" size_t lp_nms_topk_workspace_bytes(int N, int J, int H, int W, int K)
     if (N <= 0 || J <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     const int sr = strip_rows(W);
     const int nstrips = ((H + sr - 1) / sr + TK_SPB - 1) / TK_SPB;   // bands of TK_SPB strips
-    return (size_t)N * J * nstrips * K * sizeof(unsigned long long);
+    // per-warp candidate lists + one running threshold per plane
+    return (size_t)N * J * nstrips * TK_WARPS * K * sizeof(unsigned long long) + (size_t)N * J * sizeof(unsigned long long);
 }
 
 extern "C" int lp_nms_topk_f32(const float* det, const float* tag, int N, int J, int H, int W, int T, int nms_kernel,
@@ -229,7 +243,7 @@ extern "C" int lp_nms_topk_f32(const float* det, const float* tag, int N, int J,
     const int R = nms_kernel / 2;
     const int sr = strip_rows(W);
     const int nstrips = ((H + sr - 1) / sr + TK_SPB - 1) / TK_SPB;   // bands of TK_SPB strips
-    LP_CHECK_ARG(nstrips <= 256 && W <= TK_MAXW, "lp_nms_topk_f32: plane too large (H=%d W=%d)", H, W);
+    LP_CHECK_ARG(nstrips * TK_WARPS <= 256, "lp_nms_topk_f32: plane too large (H=%d W=%d)", H, W);
     const size_t need = lp_nms_topk_workspace_bytes(N, J, H, W, K);
     if (workspace_bytes < need) {
         set_error("lp_nms_topk_f32: workspace %zu < required %zu bytes", workspace_bytes, need);
@@ -242,11 +256,13 @@ extern "C" int lp_nms_topk_f32(const float* det, const float* tag, int N, int J,
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(nms_topk)");
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(nstrips, N * J);
-    nms_topk_strip_kernel<<<grid, TK_THREADS, smem, s>>>(det, H, W, R, sr, K,
-                                                          reinterpret_cast<unsigned long long*>(workspace));
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(workspace);
+    unsigned long long* plane_thr = lists + (size_t)N * J * nstrips * TK_WARPS * K;
+    cudaError_t em = cudaMemsetAsync(plane_thr, 0, (size_t)N * J * sizeof(unsigned long long), s);
+    if (em != cudaSuccess) return cuda_fail(em, "cudaMemsetAsync(plane_thr)");
+    nms_topk_strip_kernel<<<grid, TK_THREADS, smem, s>>>(det, H, W, R, sr, K, lists, plane_thr);
     LP_LAUNCH_CHECK("nms_topk_strip_kernel");
-    topk_merge_kernel<<<N * J, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(workspace), tag, H * W, T, nstrips, K,
-                                           val_k, ind_k, tag_k);
+    topk_merge_kernel<<<N * J, 32, 0, s>>>(lists, tag, H * W, T, nstrips * TK_WARPS, K, val_k, ind_k, tag_k);
     LP_LAUNCH_CHECK("topk_merge_kernel");
     return LP_OK;
 }

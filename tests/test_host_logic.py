@@ -48,7 +48,7 @@ def test_host_side_packers_and_errors():
     assert b"lp_pw1x1_pack" in lib.lp_last_error()
     # deconv program: 9 shifts per 64-channel block, 16 (phase, tap) weight tiles per block
     assert lib.lp_deconv_packed_elems(120, 48, 32) == (2 + 1) * 16 * 32 * 64
-    assert lib.lp_nms_topk_workspace_bytes(2, 14, 512, 512, 30) == 2 * 14 * 8 * 30 * 8   # 32 strips in bands of 4
+    assert lib.lp_nms_topk_workspace_bytes(2, 14, 512, 512, 30) == 2 * 14 * 8 * 8 * 30 * 8 + 2 * 14 * 8   # bands x warps lists + thresholds
 
 
 def test_config_mirrors_reference_values():
