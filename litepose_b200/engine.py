@@ -223,8 +223,9 @@ class LitePoseEngine(object):
         plan.update({"ops": ops, "outs": outs, "keep": keep, "graph": None, "static_in": None})
         return plan
 
-    def plan_for(self, n, h, w, in_dtype, out_fp32):
-        key = (n, h, w, in_dtype, out_fp32)
+    def plan_for(self, n, h, w, in_dtype, out_fp32, flip=False):
+        # the flip pass owns its own buffers so that both passes can be in flight at once
+        key = (n, h, w, in_dtype, out_fp32, bool(flip))
         pl = self.plans.get(key)
         if pl is None:
             pl = self._build_plan(n, h, w, in_dtype, out_fp32)
@@ -246,14 +247,14 @@ class LitePoseEngine(object):
             x = x.float()
         x = x.contiguous()
         n, _, h, w = x.shape
-        plan = self.plan_for(n, h, w, x.dtype, out_fp32)
+        plan = self.plan_for(n, h, w, x.dtype, out_fp32, flip)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             if self.use_graphs:
                 g = plan["graph"]
                 if g is None:
                     g = plan["graph"] = {}
-                key = bool(flip)
+                key = 0
                 if plan["static_in"] is None:
                     plan["static_in"] = torch.empty_like(x)
                 plan["static_in"].copy_(x)

@@ -87,20 +87,29 @@ class LitePosePipeline(object):
         self.adjust, self.refine = bool(cfg.TEST.ADJUST), bool(cfg.TEST.REFINE)
         self.fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device=self.device)
         self.use_graphs = use_graphs
+        import os
+        self.two_streams = os.environ.get("LP_TWO_STREAMS", "1") != "0"
         self.keep = keep                  # persons copied back per image in the fixed-size D2H payload
         self._state = {}
 
     # -- device step (everything between the H2D copy and the D2H copy) -------------
     def _device_step(self, st, x):
         eng, J = self.engine, self.params.num_joints
-        o = eng.run(x, flip=False, out_fp32=True, clone=False)
+        if self.flip and self.two_streams:
+            # the plain and the mirrored pass are independent until the glue: fork onto a side stream so that one pass'
+            # kernels fill the launch gaps and tails of the other (each pass has its own plan buffers)
+            main = torch.cuda.current_stream()
+            side = st["side"]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                f = eng.run(x, flip=True, out_fp32=True, clone=False)
+            o = eng.run(x, flip=False, out_fp32=True, clone=False)
+            main.wait_stream(side)
+        else:
+            o = eng.run(x, flip=False, out_fp32=True, clone=False)
+            if self.flip:
+                f = eng.run(x, flip=True, out_fp32=True, clone=False)
         o0, o1 = o[0], o[1]
-        if self.flip:
-            # the two passes share plan buffers: keep the plain pass' outputs
-            st["o0"].copy_(o0)
-            st["o1"].copy_(o1)
-            o0, o1 = st["o0"], st["o1"]
-            f = eng.run(x, flip=True, out_fp32=True, clone=False)
         n, _, h, w = o0.shape
         Hd, Wd = st["det"].shape[2], st["det"].shape[3]
         _lib.check(self.lib.lp_glue_f32(o0.data_ptr(), o1.data_ptr(), f[0].data_ptr() if self.flip else None,
@@ -127,8 +136,7 @@ class LitePosePipeline(object):
             row = J * (3 + T)
             st = {
                 "x": torch.empty((n, 3, s_h, s_w), dtype=dtype, device=dev),
-                "o0": torch.empty((n, 2 * J, s_h // 4, s_w // 4), dtype=torch.float32, device=dev),
-                "o1": torch.empty((n, J, s_h // 2, s_w // 2), dtype=torch.float32, device=dev),
+                "side": torch.cuda.Stream(device=dev),
                 "det": torch.empty((n, J, Hd, Wd), dtype=torch.float32, device=dev),
                 "tag": torch.empty((n, J, Hd, Wd, T), dtype=torch.float32, device=dev),
                 "packed": torch.zeros((n, self.keep * row + self.keep + 1), dtype=torch.float32, device=dev),
