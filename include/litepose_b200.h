@@ -125,6 +125,21 @@ int lp_head_pack(const uint16_t* w1, const uint16_t* w2, int C1, int C2, int Co,
 int lp_head_pw_dual_f16(const void* a1, const void* a2, const void* w_packed, void* out_nchw,
                         int out_fp32, int N, int H, int W, int C1, int C2, int Co, lp_stream_t stream);
 
+/* ---- M4 fused: both SepConv2d heads of one level in ONE kernel -------------------
+ * out_nchw[N,Co,H,W] = W1 * relu(dw5x5(a1) + b1) + W2 * relu(dw5x5(a2) + b2)
+ * (final_refined[i](refined) + final_raw[i](raw), lib/models/pose_mobilenet.py:151-154,
+ * lib/models/layers/layers.py:120-133): depthwise 5x5 on the CUDA cores, result kept in shared
+ * memory as the tcgen05 A operand, bias-free 1x1 on the tensor cores, NCHW fp32/fp16 store.
+ * Pack (host memory): dw1/dw2 tap-major [25][C] BN-folded fp16 + fp32 biases, w1 [Co][C1], w2 [Co][C2]. */
+size_t lp_head_fused_dw_elems(int C1, int C2);           /* fp16 elements of dw_cat; bias: /25 fp32 */
+size_t lp_head_fused_pw_elems(int C1, int C2, int Co);   /* fp16 elements of pw_packed */
+int lp_head_fused_pack(const uint16_t* dw1, const float* bdw1, const uint16_t* dw2, const float* bdw2,
+                       const uint16_t* w1, const uint16_t* w2, int C1, int C2, int Co, uint16_t* dw_cat,
+                       float* bdw_cat, uint16_t* pw_packed);
+int lp_head_fused_f16(const void* a1, const void* a2, const void* dw_cat, const float* bdw_cat,
+                      const void* pw_packed, void* out_nchw, int out_fp32, int N, int H, int W, int C1,
+                      int C2, int Co, lp_stream_t stream);
+
 /* ---- G1+G2: NMS (k x k window max, -inf padding) + top-K per (n,j) plane -----
  * det fp32 [N,J,H,W]; tag fp32 [N,J,H,W,T].  Order: value desc, flat index asc over
  * NMS survivors with value > 0; unused slots are (0.0f, index 0).

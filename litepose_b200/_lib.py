@@ -50,6 +50,10 @@ SIGNATURES = {
     "lp_head_packed_elems": (_sz, [_i, _i, _i]),
     "lp_head_pack": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "lp_head_pw_dual_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lp_head_fused_dw_elems": (_sz, [_i, _i]),
+    "lp_head_fused_pw_elems": (_sz, [_i, _i, _i]),
+    "lp_head_fused_pack": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "lp_head_fused_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lp_nms_topk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "lp_nms_topk_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lp_tag_match_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -18,10 +18,13 @@
 namespace lp {
 
 constexpr int FP_T = 16;                         // output tile side
-constexpr int FP_I = FP_T + 6;                   // haloed input side (k = 7)
 constexpr int FP_CB = 32;                        // channels per slab
-constexpr int FP_IN_BYTES = FP_I * FP_I * FP_CB * 2;          // 30976
-constexpr int FP_W_BYTES = 49 * FP_CB * 2;                     // depthwise weights of one slab, 3136 B
+template <int K> struct FpCfg {
+    static constexpr int I = FP_T + K - 1;                       // haloed input side (22 for k = 7, 20 for k = 5)
+    static constexpr int IN_BYTES = I * I * FP_CB * 2;           // 30976 / 25600
+    static constexpr int W_BYTES = K * K * FP_CB * 2;            // depthwise weights of one slab: 3136 / 1600 B
+    static constexpr int IR = 4 + K - 1;                         // input rows / columns of a 4x4 micro-block
+};
 constexpr int FP_IN_STRIDE = 35840;                           // ring pitch: input tile + weight slab (multiple of 1024)
 constexpr int FP_W_OFF = 31744;                               // weights inside a ring stage (128-byte aligned)
 constexpr int FP_NIN = 4;                                      // slab ring: even slabs use stages 0/2, odd 1/3
@@ -30,7 +33,7 @@ constexpr int FP_NB = 2;
 constexpr int FP_B_BYTES = 160 * 64 * 2;                      // Co <= 160
 constexpr int FP_DW_WARPS = 16;                                // two groups of 8: even / odd 32-channel slabs
 constexpr int FP_THREADS = (FP_DW_WARPS + 2) * 32;
-static_assert(FP_W_OFF >= FP_IN_BYTES && FP_W_OFF + FP_W_BYTES <= FP_IN_STRIDE, "ring stage layout");
+static_assert(FP_W_OFF >= FpCfg<7>::IN_BYTES && FP_W_OFF + FpCfg<7>::W_BYTES <= FP_IN_STRIDE, "ring stage layout");
 constexpr int FP_MAX_CE = 1024;
 constexpr size_t FP_SMEM = (size_t)FP_NIN * FP_IN_STRIDE + 2 * FP_A_TILE + FP_NB * FP_B_BYTES + 1024 + FP_MAX_CE * 4 + 1024;
 
@@ -46,11 +49,13 @@ struct FpParams {
     int N, H, W, Ce, Co, n_tile;      // n_tile = round_up(Co, 16)
     int tiles_x, tiles_y, num_tiles;
     int nslabs, nkb;
-    const __half* w_dw;               // [49][Ce]
-    const float* b_dw;                // [Ce]
+    int ns0;                          // slabs taken from the first source (HEAD mode: the rest come from the second)
+    int out_fp32;                     // HEAD mode: NCHW output dtype
+    const __half* w_dw;               // [k*k][Ce]
+    const float* b_dw;                // [Ce] (HEAD mode: padded per slab, nslabs*32)
     const float* b_pj;                // packed, n_tile
     const __half* residual;           // [N,H,W,Co] or null
-    __half* out;                      // [N,H,W,Co]
+    void* out;                        // [N,H,W,Co] fp16 (HEAD: [N,Co,H,W] fp32/fp16)
 };
 
 __device__ __forceinline__ float fp_fhfma(unsigned short a, unsigned short b, float c) {
@@ -61,9 +66,15 @@ __device__ __forceinline__ float fp_fhfma(unsigned short a, unsigned short b, fl
 __device__ __forceinline__ unsigned short fp_lo(__half2 v) { return __half_as_ushort(__low2half(v)); }
 __device__ __forceinline__ unsigned short fp_hi(__half2 v) { return __half_as_ushort(__high2half(v)); }
 
+// HEAD = 0: block projection (ReLU6 after the depthwise, NHWC fp16 output with bias and optional residual).
+// HEAD = 1: output head (two sources, ReLU after the depthwise, bias-free 1x1, NCHW fp32/fp16 output).
+template <int K, int HEAD>
 __global__ void __launch_bounds__(FP_THREADS, 1)
-dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                   const __grid_constant__ CUtensorMap map_dw, const __grid_constant__ FpParams p) {
+dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x1,
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dw,
+                  const __grid_constant__ FpParams p) {
+    using Cfg = FpCfg<K>;
+    constexpr int FP_I = Cfg::I;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sIn = smem;                                         // FP_NIN x [22][22][32] fp16
     uint8_t* sA = smem + FP_NIN * FP_IN_STRIDE;                  // [mtile 2] x 16 KiB, 128B-swizzled
@@ -73,10 +84,10 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     FpBars* bars = reinterpret_cast<FpBars*>(sBdw + FP_MAX_CE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int K = 7;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&map_x);
+        if (HEAD) tma_prefetch_desc(&map_x1);
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_dw);
         for (int i = 0; i < FP_NIN; ++i) { mbar_init(&bars->in_full[i], 1); mbar_init(&bars->in_empty[i], 8); }
@@ -92,7 +103,8 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tc_relinquish();
     }
     for (int i = threadIdx.x; i < p.n_tile; i += FP_THREADS) sBias[i] = p.b_pj ? p.b_pj[i] : 0.f;
-    for (int i = threadIdx.x; i < p.nslabs * FP_CB; i += FP_THREADS) sBdw[i] = (p.b_dw && i < p.Ce) ? p.b_dw[i] : 0.f;
+    for (int i = threadIdx.x; i < p.nslabs * FP_CB; i += FP_THREADS)
+        sBdw[i] = (p.b_dw && (HEAD || i < p.Ce)) ? p.b_dw[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -114,9 +126,10 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const int g = s & 1;                              // even / odd slab group, stages g and g+2
                     const uint32_t is = 2 * (iu[g] & 1) + g;
                     mbar_wait(&bars->in_empty[is], ((iu[g] >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&bars->in_full[is], FP_IN_BYTES + FP_W_BYTES);
-                    tma_load_4d(sIn + is * FP_IN_STRIDE, &map_x, &bars->in_full[is], s * FP_CB, tx * FP_T - 3,
-                                ty * FP_T - 3, n);
+                    mbar_expect_tx(&bars->in_full[is], Cfg::IN_BYTES + Cfg::W_BYTES);
+                    const bool second = HEAD && s >= p.ns0;
+                    tma_load_4d(sIn + is * FP_IN_STRIDE, second ? &map_x1 : &map_x, &bars->in_full[is],
+                                (second ? s - p.ns0 : s) * FP_CB, tx * FP_T - K / 2, ty * FP_T - K / 2, n);
                     tma_load_2d(sIn + is * FP_IN_STRIDE + FP_W_OFF, &map_dw, &bars->in_full[is], s * FP_CB, 0);
                     ++iu[g];
                 }
@@ -135,8 +148,7 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     mbar_wait(&bars->a_full, kbc & 1);
                     mbar_wait(&bars->b_full[bs], bph);
                     tc_fence_after();
-                    const int chans = min(64, p.Ce - kb * 64);
-                    const int k16 = (chans + 15) >> 4;
+                    const int k16 = 2 * min(2, p.nslabs - 2 * kb);      // 32 channels per slab present in this K block
                     const uint32_t b_base = smem_u32(sB + bs * FP_B_BYTES);
                     for (int mt = 0; mt < 2; ++mt) {
                         const uint32_t a_base = smem_u32(sA + mt * FP_A_TILE);
@@ -193,12 +205,12 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             for (int kx = 0; kx < K; ++kx) wreg[ky * K + kx] = ws[ky * K * (FP_CB / 2) + kx * wstep];
                     }
                     const __half2* tile_in = reinterpret_cast<const __half2*>(sIn + is * FP_IN_STRIDE);
-                    const __half2* base = tile_in + (oy * FP_I + ox + (mir ? 9 : 0)) * (FP_CB / 2) + cp;
+                    const __half2* base = tile_in + (oy * FP_I + ox + (mir ? Cfg::IR - 1 : 0)) * (FP_CB / 2) + cp;
 #pragma unroll
-                    for (int r = 0; r < 10; ++r) {
-                        __half2 in[10];
+                    for (int r = 0; r < Cfg::IR; ++r) {
+                        __half2 in[Cfg::IR];
 #pragma unroll
-                        for (int c = 0; c < 10; ++c) in[c] = base[r * FP_I * (FP_CB / 2) + c * cstep];
+                        for (int c = 0; c < Cfg::IR; ++c) in[c] = base[r * FP_I * (FP_CB / 2) + c * cstep];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int ky = r - i;
@@ -230,8 +242,9 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int r = ((oy + i) & 7) * 16 + ox + (mir ? 3 - j : j);     // row inside the M-tile
-                            const __half2 v = __floats2half2_rn(fminf(fmaxf(acc[i][j].x, 0.f), 6.f),
-                                                                fminf(fmaxf(acc[i][j].y, 0.f), 6.f));
+                            const float hi = HEAD ? 3.0e38f : 6.f;     // ReLU (heads) / ReLU6 (blocks)
+                            const __half2 v = __floats2half2_rn(fminf(fmaxf(acc[i][j].x, 0.f), hi),
+                                                                fminf(fmaxf(acc[i][j].y, 0.f), hi));
                             *reinterpret_cast<__half2*>(a_mt + r * 128 + ((jch ^ (r & 7)) << 4) + ((cp & 3) << 2)) = v;
                         }
                     fence_proxy_async();
@@ -254,6 +267,24 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 for (int c0 = chalf * 16; c0 < p.n_tile; c0 += 32) {
                     tc_ld16(taddr + c0, r);
                     tc_wait_ld();
+                    if (HEAD) {
+                        if (valid) {
+                            const size_t plane = (size_t)p.H * p.W;
+                            const size_t o = ((size_t)n * p.Co + c0) * plane + (size_t)gy * p.W + gx;
+                            if (p.out_fp32) {
+                                float* op = reinterpret_cast<float*>(p.out) + o;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (c0 + i < p.Co) op[(size_t)i * plane] = __uint_as_float(r[i]);
+                            } else {
+                                __half* op = reinterpret_cast<__half*>(p.out) + o;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (c0 + i < p.Co) op[(size_t)i * plane] = __float2half_rn(__uint_as_float(r[i]));
+                            }
+                        }
+                        continue;
+                    }
                     if (valid && c0 < p.Co) {
                         float v[16];
 #pragma unroll
@@ -288,7 +319,7 @@ dw7_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                             ph0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
                             ph1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
                         }
-                        uint4* op = reinterpret_cast<uint4*>(p.out + off + c0);
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off + c0);
                         op[0] = o0;
                         if (two) op[1] = o1;
                     }
@@ -340,12 +371,13 @@ extern "C" int lp_dw7_project_f16(const void* x, const void* w_dw, const float* 
     p.b_dw = b_dw;
     p.b_pj = b_proj_packed;
     p.residual = reinterpret_cast<const __half*>(residual);
-    p.out = reinterpret_cast<__half*>(out);
+    p.out = out;
+    p.ns0 = p.nslabs;
     CUtensorMap mx, mw;
     {
         uint64_t dims[4] = {(uint64_t)Ce, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         uint64_t strides[3] = {(uint64_t)Ce * 2, (uint64_t)W * Ce * 2, (uint64_t)H * W * Ce * 2};
-        uint32_t box[4] = {(uint32_t)FP_CB, (uint32_t)FP_I, (uint32_t)FP_I, 1u};
+        uint32_t box[4] = {(uint32_t)FP_CB, (uint32_t)FpCfg<7>::I, (uint32_t)FpCfg<7>::I, 1u};
         int rc = make_tmap(&mx, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         // packed projection weights: [kb][n_tile][64] (lp_pw1x1_pack with a single N chunk since Co <= 160)
@@ -363,11 +395,115 @@ extern "C" int lp_dw7_project_f16(const void* x, const void* w_dw, const float* 
         int rc = make_tmap(&md, w_dw, 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     }
-    cudaError_t e = cudaFuncSetAttribute((const void*)dw7_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute((const void*)dw_project_kernel<7, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FP_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw7_project)");
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    dw7_project_kernel<<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(mx, mw, md, p);
-    LP_LAUNCH_CHECK("dw7_project_kernel");
+    dw_project_kernel<7, 0><<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(mx, mx, mw, md, p);
+    LP_LAUNCH_CHECK("dw_project_kernel<7,0>");
+    return LP_OK;
+}
+
+// ------------------------------------------------------------------ fused output head (M4)
+static int head_slabs(int C) { return (C + FP_CB - 1) / FP_CB; }
+
+extern "C" size_t lp_head_fused_dw_elems(int C1, int C2) { return (size_t)25 * (head_slabs(C1) + head_slabs(C2)) * FP_CB; }
+extern "C" size_t lp_head_fused_pw_elems(int C1, int C2, int Co) {
+    const int ns = head_slabs(C1) + head_slabs(C2);
+    return (size_t)((ns + 1) / 2) * ((Co + 15) / 16 * 16) * 64;
+}
+// dw1/dw2: tap-major [25][C] BN-folded depthwise weights, bdw1/bdw2 their biases; w1 [Co][C1], w2 [Co][C2].
+// Outputs (host): dw_cat [25][ns*32] fp16, bdw_cat [ns*32] fp32, pw_packed [kb][n_tile][64] fp16 in slab order.
+extern "C" int lp_head_fused_pack(const uint16_t* dw1, const float* bdw1, const uint16_t* dw2, const float* bdw2,
+                                  const uint16_t* w1, const uint16_t* w2, int C1, int C2, int Co, uint16_t* dw_cat,
+                                  float* bdw_cat, uint16_t* pw_packed) {
+    LP_CHECK_ARG(dw1 && dw2 && w1 && w2 && dw_cat && bdw_cat && pw_packed && C1 > 0 && C2 > 0 && Co > 0,
+                 "lp_head_fused_pack: bad args");
+    const int s1 = head_slabs(C1), s2 = head_slabs(C2), ns = s1 + s2, CP = ns * FP_CB;
+    const int nt = (Co + 15) / 16 * 16, nkb = (ns + 1) / 2;
+    for (int t = 0; t < 25; ++t)
+        for (int c = 0; c < CP; ++c) {
+            const bool second = c >= s1 * FP_CB;
+            const int cc = second ? c - s1 * FP_CB : c;
+            const int C = second ? C2 : C1;
+            dw_cat[(size_t)t * CP + c] = cc < C ? (second ? dw2 : dw1)[(size_t)t * C + cc] : (uint16_t)0;
+        }
+    for (int c = 0; c < CP; ++c) {
+        const bool second = c >= s1 * FP_CB;
+        const int cc = second ? c - s1 * FP_CB : c;
+        const float* b = second ? bdw2 : bdw1;
+        bdw_cat[c] = (b && cc < (second ? C2 : C1)) ? b[cc] : 0.f;
+    }
+    for (int kb = 0; kb < nkb; ++kb)
+        for (int r = 0; r < nt; ++r)
+            for (int kk = 0; kk < 64; ++kk) {
+                const int c = kb * 64 + kk;                    // padded concatenated channel
+                uint16_t v = 0;
+                if (r < Co && c < CP) {
+                    const bool second = c >= s1 * FP_CB;
+                    const int cc = second ? c - s1 * FP_CB : c;
+                    if (cc < (second ? C2 : C1)) v = (second ? w2 : w1)[(size_t)r * (second ? C2 : C1) + cc];
+                }
+                pw_packed[((size_t)kb * nt + r) * 64 + kk] = v;
+            }
+    return LP_OK;
+}
+
+// out[N,Co,H,W] = W1 * relu(dw5(a1) + b1) + W2 * relu(dw5(a2) + b2): both SepConv2d heads of one level in ONE kernel
+// (reference lib/models/pose_mobilenet.py:151-154, lib/models/layers/layers.py:120-133).
+extern "C" int lp_head_fused_f16(const void* a1, const void* a2, const void* dw_cat, const float* bdw_cat,
+                                 const void* pw_packed, void* out_nchw, int out_fp32, int N, int H, int W, int C1, int C2,
+                                 int Co, lp_stream_t stream) {
+    LP_CHECK_ARG(a1 && a2 && dw_cat && bdw_cat && pw_packed && out_nchw, "lp_head_fused_f16: null pointer");
+    LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 > 0 && Co > 0 && Co <= 160,
+                 "lp_head_fused_f16: bad shape N=%d H=%d W=%d C1=%d C2=%d Co=%d", N, H, W, C1, C2, Co);
+    if ((reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(a2) | reinterpret_cast<uintptr_t>(dw_cat) |
+         reinterpret_cast<uintptr_t>(pw_packed)) & 15) {
+        set_error("lp_head_fused_f16: pointers must be 16-byte aligned");
+        return LP_ERR_ALIGN;
+    }
+    FpParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.H = H; p.W = W; p.Co = Co;
+    p.ns0 = head_slabs(C1);
+    p.nslabs = p.ns0 + head_slabs(C2);
+    p.Ce = p.nslabs * FP_CB;
+    LP_CHECK_ARG(p.Ce <= FP_MAX_CE, "lp_head_fused_f16: too many channels");
+    p.nkb = (p.nslabs + 1) / 2;
+    p.n_tile = (Co + 15) / 16 * 16;
+    p.tiles_x = (W + FP_T - 1) / FP_T;
+    p.tiles_y = (H + FP_T - 1) / FP_T;
+    p.num_tiles = p.tiles_x * p.tiles_y * N;
+    p.w_dw = reinterpret_cast<const __half*>(dw_cat);
+    p.b_dw = bdw_cat;
+    p.out = out_nchw;
+    p.out_fp32 = out_fp32;
+    CUtensorMap m0, m1, mw, md;
+    for (int i = 0; i < 2; ++i) {
+        const int C = i ? C2 : C1;
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+        uint32_t box[4] = {(uint32_t)FP_CB, (uint32_t)FpCfg<5>::I, (uint32_t)FpCfg<5>::I, 1u};
+        int rc = make_tmap(i ? &m1 : &m0, i ? a2 : a1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
+    {
+        uint64_t d2[2] = {64u, (uint64_t)p.nkb * p.n_tile};
+        uint64_t s2[1] = {128u};
+        uint32_t b2[2] = {64u, (uint32_t)p.n_tile};
+        int rc = make_tmap(&mw, pw_packed, 2, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        uint64_t d3[2] = {(uint64_t)p.Ce, 25u};
+        uint64_t s3[1] = {(uint64_t)p.Ce * 2};
+        uint32_t b3[2] = {(uint32_t)FP_CB, 25u};
+        rc = make_tmap(&md, dw_cat, 2, d3, s3, b3, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void*)dw_project_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FP_SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(head_fused)");
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    dw_project_kernel<5, 1><<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(m0, m1, mw, md, p);
+    LP_LAUNCH_CHECK("dw_project_kernel<5,1>");
     return LP_OK;
 }

@@ -47,6 +47,7 @@ class LitePoseEngine(object):
         self.use_graphs = False
         import os
         self.fuse_dw_project = os.environ.get("LP_FUSE_DW_PROJECT", "1") != "0"
+        self.fuse_heads = os.environ.get("LP_FUSE_HEADS", "1") != "0"
         sd = {k: v.detach() for k, v in state_dict.items()}
         self._prep(sd)
 
@@ -126,6 +127,19 @@ class LitePoseEngine(object):
                 _lib.check(self.lib.lp_head_pack(a.ctypes.data, c.ctypes.data, c1, c2, co, wp.ctypes.data),
                            "lp_head_pack")
                 hd.update({"w": self._dev(wp, torch.float16), "C1": c1, "C2": c2, "Co": co})
+                # fused head: concatenated depthwise slabs + slab-ordered 1x1 weights
+                d1, d2 = hd["final_refined_dw"], hd["final_raw_dw"]
+                dwc = np.zeros(self.lib.lp_head_fused_dw_elems(c1, c2), np.uint16)
+                bdc = np.zeros(dwc.size // 25, np.float32)
+                pwc = np.zeros(self.lib.lp_head_fused_pw_elems(c1, c2, co), np.uint16)
+                x1, x2 = _np16(d1["w"].float()), _np16(d2["w"].float())
+                y1 = np.ascontiguousarray(d1["b"].cpu().numpy())
+                y2 = np.ascontiguousarray(d2["b"].cpu().numpy())
+                _lib.check(self.lib.lp_head_fused_pack(x1.ctypes.data, y1.ctypes.data, x2.ctypes.data, y2.ctypes.data,
+                                                       a.ctypes.data, c.ctypes.data, c1, c2, co, dwc.ctypes.data,
+                                                       bdc.ctypes.data, pwc.ctypes.data), "lp_head_fused_pack")
+                hd.update({"dw_cat": self._dev(dwc, torch.float16), "bdw_cat": self._dev(bdc, torch.float32),
+                           "pw_cat": self._dev(pwc, torch.float16)})
                 P["heads"].append(hd)
         self.P = P
 
@@ -208,18 +222,24 @@ class LitePoseEngine(object):
             raw = x_list[-i - 3][0]
             if i > 0:
                 hd = P["heads"][i - 1]
-                t1, t2 = buf(n, rh, rw, hd["C1"]), buf(n, rh, rw, hd["C2"])
-                keep += [t1, t2]
-                for src, dst, key in ((refined, t1, "final_refined_dw"), (raw, t2, "final_raw_dw")):
-                    dd = hd[key]
-                    ops.append(_Op("head_dw", lib.lp_dwconv_f16,
-                                   [src.data_ptr(), dd["w"].data_ptr(), dd["b"].data_ptr(), dst.data_ptr(), n,
-                                    dd["C"], rh, rw, dd["k"], 1, _lib.ACT_RELU]))
                 o = torch.empty((n, hd["Co"], rh, rw), dtype=torch.float32 if out_fp32 else f16, device=dev)
                 outs.append(o)
-                ops.append(_Op("head_pw", lib.lp_head_pw_dual_f16,
-                               [t1.data_ptr(), t2.data_ptr(), hd["w"].data_ptr(), o.data_ptr(), 1 if out_fp32 else 0,
-                                n, rh, rw, hd["C1"], hd["C2"], hd["Co"]]))
+                if self.fuse_heads:
+                    ops.append(_Op("head_fused", lib.lp_head_fused_f16,
+                                   [refined.data_ptr(), raw.data_ptr(), hd["dw_cat"].data_ptr(),
+                                    hd["bdw_cat"].data_ptr(), hd["pw_cat"].data_ptr(), o.data_ptr(),
+                                    1 if out_fp32 else 0, n, rh, rw, hd["C1"], hd["C2"], hd["Co"]]))
+                else:
+                    t1, t2 = buf(n, rh, rw, hd["C1"]), buf(n, rh, rw, hd["C2"])
+                    keep += [t1, t2]
+                    for src, dst, key in ((refined, t1, "final_refined_dw"), (raw, t2, "final_raw_dw")):
+                        dd = hd[key]
+                        ops.append(_Op("head_dw", lib.lp_dwconv_f16,
+                                       [src.data_ptr(), dd["w"].data_ptr(), dd["b"].data_ptr(), dst.data_ptr(), n,
+                                        dd["C"], rh, rw, dd["k"], 1, _lib.ACT_RELU]))
+                    ops.append(_Op("head_pw", lib.lp_head_pw_dual_f16,
+                                   [t1.data_ptr(), t2.data_ptr(), hd["w"].data_ptr(), o.data_ptr(),
+                                    1 if out_fp32 else 0, n, rh, rw, hd["C1"], hd["C2"], hd["Co"]]))
         plan.update({"ops": ops, "outs": outs, "keep": keep, "graph": None, "static_in": None})
         return plan
 

@@ -184,3 +184,44 @@ def test_dw7_project_fused(n, h, w, ce, co, res):
                                       stream()), "dw7_project")
     torch.cuda.synchronize()
     tol_check(from_nhwc(out), ref, what="dw7_project ce%d co%d" % (ce, co))
+
+
+@pytest.mark.parametrize("n,h,w,c1,c2,co,fp32", [
+    (2, 32, 32, 24, 16, 28, True), (1, 64, 64, 32, 16, 14, True), (1, 48, 16, 40, 24, 28, False),
+    (2, 16, 16, 64, 24, 34, True), (1, 20, 36, 24, 16, 28, True),
+])
+def test_head_fused(n, h, w, c1, c2, co, fp32):
+    """both SepConv2d heads of a level (dw5+BN+ReLU -> 1x1, two branches summed) in one kernel"""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(c1 * 7 + c2 + co)
+    x1 = q16(torch.randn(n, c1, h, w, generator=g))
+    x2 = q16(torch.randn(n, c2, h, w, generator=g))
+    d1 = q16(torch.randn(c1, 1, 5, 5, generator=g) * 0.2)
+    d2 = q16(torch.randn(c2, 1, 5, 5, generator=g) * 0.2)
+    b1, b2 = torch.randn(c1, generator=g) * 0.1, torch.randn(c2, generator=g) * 0.1
+    w1 = q16(torch.randn(co, c1, generator=g) / (c1 ** 0.5))
+    w2 = q16(torch.randn(co, c2, generator=g) / (c2 ** 0.5))
+    m1 = q16(F.relu(F.conv2d(x1, d1, b1, 1, 2, 1, c1)))
+    m2 = q16(F.relu(F.conv2d(x2, d2, b2, 1, 2, 1, c2)))
+    ref = F.conv2d(m1, w1.view(co, c1, 1, 1)) + F.conv2d(m2, w2.view(co, c2, 1, 1))
+
+    def u16(t):
+        return np.ascontiguousarray(t.half().numpy()).view(np.uint16)
+
+    dwc = np.zeros(lib.lp_head_fused_dw_elems(c1, c2), np.uint16)
+    bdc = np.zeros(dwc.size // 25, np.float32)
+    pwc = np.zeros(lib.lp_head_fused_pw_elems(c1, c2, co), np.uint16)
+    a1, a2 = u16(d1.reshape(c1, 25).t().contiguous()), u16(d2.reshape(c2, 25).t().contiguous())
+    y1, y2 = np.ascontiguousarray(b1.numpy()), np.ascontiguousarray(b2.numpy())
+    p1, p2 = u16(w1), u16(w2)
+    _lib.check(lib.lp_head_fused_pack(a1.ctypes.data, y1.ctypes.data, a2.ctypes.data, y2.ctypes.data, p1.ctypes.data,
+                                      p2.ctypes.data, c1, c2, co, dwc.ctypes.data, bdc.ctypes.data, pwc.ctypes.data))
+    dwd = torch.from_numpy(dwc).view(torch.float16).cuda()
+    bdd = torch.from_numpy(bdc).cuda()
+    pwd = torch.from_numpy(pwc).view(torch.float16).cuda()
+    out = torch.full((n, co, h, w), float("nan"), dtype=torch.float32 if fp32 else torch.float16, device="cuda")
+    s1, s2 = nhwc16(x1), nhwc16(x2)
+    _lib.check(lib.lp_head_fused_f16(s1.data_ptr(), s2.data_ptr(), dwd.data_ptr(), bdd.data_ptr(), pwd.data_ptr(),
+                                     out.data_ptr(), 1 if fp32 else 0, n, h, w, c1, c2, co, stream()), "head_fused")
+    torch.cuda.synchronize()
+    tol_check(out, ref, what="head_fused c1 %d c2 %d co %d" % (c1, c2, co))
