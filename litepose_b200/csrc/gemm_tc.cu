@@ -25,7 +25,8 @@ constexpr int A_BYTES = BM * BK * 2;    // 16 KiB
 constexpr int B_BYTES = 256 * BK * 2;   // 32 KiB
 constexpr int STAGES = 3;        // MODE_PW (plus OUT_BYTES of output staging)
 constexpr int STAGES_NOSTAGE = 4; // MODE_DECONV / MODE_HEAD (no staging buffer)
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 9;      // resident-weights mode: the whole ring area minus the weights holds 16 KiB A stages
+constexpr int RING_BYTES = STAGES * (A_BYTES + B_BYTES);   // 144 KiB
 constexpr int OUT_SUB = 128 * 64 * 2;   // one 128-row x 64-column fp16 output sub-tile (128B-swizzled), 16 KiB
 constexpr int OUT_BYTES = 4 * OUT_SUB;  // staging for up to 256 output columns
 constexpr int MAX_STEPS = 48;
@@ -53,6 +54,9 @@ struct GemmParams {
     int n_tile;        // MMA N (multiple of 16, <= 256)
     int num_steps;
     int total_bt;      // weight sub-tiles per chunk
+    int b_resident;    // MODE_PW: all K blocks of the CTA's N chunk stay in shared memory, only A tiles stream
+    int nst_a;         // MODE_PW resident mode: number of 16 KiB A stages
+    int m_tiles;
     int M, N;          // PW: rows, real out channels.  spatial modes: N = Co
     int act;
     int H, W, TH, TW, tiles_x, tiles_y;  // spatial modes
@@ -68,6 +72,7 @@ struct __align__(8) GemmBarriers {
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint64_t res_full;
+    uint64_t bres_full;
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -99,7 +104,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (p.residual) tma_prefetch_desc(&mapRes);
         }
         mbar_init(&bars->res_full, 1);
-        for (int i = 0; i < NST; ++i) {
+        mbar_init(&bars->bres_full, 1);
+        for (int i = 0; i < MAX_STAGES; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->empty[i], 1);
         }
@@ -122,13 +128,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
+    // Work distribution.  Streaming mode: item t -> (m-tile t / n_chunks, chunk t %% n_chunks), strided over the grid.
+    // Resident-weights mode (MODE_PW): the CTA keeps ONE N chunk for its whole life (its weights are loaded once),
+    // the CTAs sharing a chunk split the m-tiles round-robin.
+    const bool resident = (MODE == MODE_PW) && p.b_resident;
+    const int cpc = resident ? (int)gridDim.x / p.n_chunks : 1;           // CTAs per chunk
+    const int my_chunk = resident ? (int)blockIdx.x % p.n_chunks : 0;
+    const int t_begin = resident ? (int)blockIdx.x / p.n_chunks : (int)blockIdx.x;
+    const int t_end = resident ? p.m_tiles : p.num_tiles;
+    const int t_step = resident ? cpc : (int)gridDim.x;
+    // resident mode: weights at the start of the ring area, A stages behind them
+    const int bres_bytes = resident ? ((p.num_steps * p.n_tile * (BK * 2) + 1023) & ~1023) : 0;
+    uint8_t* sAres = smem + bres_bytes;
+    const int nst = resident ? p.nst_a : NST;
+
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                const int chunk = t % p.n_chunks;
-                const int mt = t / p.n_chunks;
+            if (resident) {
+                mbar_expect_tx(&bars->bres_full, (uint32_t)p.num_steps * p.n_tile * (BK * 2));
+                for (int s = 0; s < p.num_steps; ++s)
+                    tma_load_2d(smem + s * p.n_tile * (BK * 2), &mapB, &bars->bres_full, 0,
+                                (my_chunk * p.total_bt + s) * p.n_tile);
+            }
+            for (int t = t_begin; t < t_end; t += t_step) {
+                const int chunk = resident ? my_chunk : t % p.n_chunks;
+                const int mt = resident ? t : t / p.n_chunks;
+                if (resident) {
+                    for (int s = 0; s < p.num_steps; ++s) {
+                        mbar_wait(&bars->empty[stage], phase ^ 1);
+                        mbar_expect_tx(&bars->full[stage], A_BYTES);
+                        tma_load_2d(sAres + stage * A_BYTES, &mapA0, &bars->full[stage], p.steps[s].kc, mt * BM);
+                        if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
                 int tx = 0, ty = 0, n = 0;
                 if (MODE != MODE_PW) {
                     tx = mt % p.tiles_x;
@@ -162,7 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t idesc = umma_idesc_f16(BM, p.n_tile);
             uint32_t stage = 0, phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            if (resident) mbar_wait(&bars->bres_full, 0);
+            for (int t = t_begin; t < t_end; t += t_step, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -171,8 +207,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const Step& st = p.steps[s];
                     mbar_wait(&bars->full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
-                    const uint32_t b_base = smem_u32(sB + stage * B_BYTES);
+                    const uint32_t a_base = smem_u32(resident ? sAres + stage * A_BYTES : sA + stage * A_BYTES);
+                    const uint32_t b_base = smem_u32(resident ? smem + s * p.n_tile * (BK * 2) : sB + stage * B_BYTES);
                     for (int j = 0; j < st.nb; ++j) {
                         const uint32_t acc = st.acc[j];
                         const uint32_t d = tmem_base + buf * 256 + acc * p.n_tile;
@@ -184,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         used |= 1u << acc;
                     }
                     tc_commit(&bars->empty[stage]);
-                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&bars->tmem_full[buf]);
             }
@@ -195,10 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int half = (warp - 2) >> 2;          // the two warps of a quarter take alternate 16-column groups
         const int row = q * 32 + lane;
         int it = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        for (int t = t_begin; t < t_end; t += t_step, ++it) {
             const int buf = it & 1;
-            const int chunk = t % p.n_chunks;
-            const int mt = t / p.n_chunks;
+            const int chunk = resident ? my_chunk : t % p.n_chunks;
+            const int mt = resident ? t : t / p.n_chunks;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
             uint32_t r[16];
             if (MODE != MODE_PW) {
@@ -423,6 +459,12 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     int rc = set_smem_attr_once((const void*)gemm_tc_kernel<MODE>);
     if (rc) return rc;
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    if (MODE == MODE_PW && p.b_resident) {
+        // a multiple of n_chunks CTAs, at most one per SM and no more CTAs per chunk than m-tiles
+        int cpc = num_sms() / p.n_chunks;
+        if (cpc > p.m_tiles) cpc = p.m_tiles;
+        grid = cpc * p.n_chunks;
+    }
     if (grid < 1) return LP_OK;
     gemm_tc_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(a0, a1, b, mo, mr, p);
     LP_LAUNCH_CHECK("gemm_tc_kernel");
@@ -481,7 +523,17 @@ extern "C" int lp_pw1x1_f16(const void* a, const void* w_packed, const float* bi
     LP_CHECK_ARG(kb <= MAX_STEPS && p.n_chunks * p.n_tile <= MAX_BIAS, "lp_pw1x1_f16: K=%d or N=%d too large", K, N);
     const int m_tiles = (M + BM - 1) / BM;
     p.num_tiles = m_tiles * p.n_chunks;
+    p.m_tiles = m_tiles;
     p.num_steps = kb;
+    {
+        // resident-weights mode when one N chunk's weights leave room for >= 5 A stages in the ring area
+        const int bres = ((kb * p.n_tile * (BK * 2)) + 1023) & ~1023;
+        const int nst = (RING_BYTES - bres) / A_BYTES;
+        if (nst >= 5 && p.n_chunks <= num_sms()) {
+            p.b_resident = 1;
+            p.nst_a = nst < MAX_STAGES ? nst : MAX_STAGES;
+        }
+    }
     p.total_bt = kb;
     p.M = M;
     p.N = N;
