@@ -2,6 +2,7 @@
 // tensor-map construction through the driver entry point (no link-time libcuda dependency).
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -79,6 +80,15 @@ int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims
         return LP_ERR_CUDA;
     }
     return LP_OK;
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LP_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 int num_sms() {

@@ -61,9 +61,11 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
     const int n = blockIdx.z;
     const int ox0 = tx * Cfg::TW, oy0 = ty * Cfg::TH;
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
+        pdl_wait();           // input activations complete (weights below are static and may be read earlier)
         mbar_expect_tx(bar, Cfg::IH * Cfg::IW * DW_CB * 2);
         tma_load_4d(smem, &map_x, bar, c0, ox0 * S - K / 2, oy0 * S - K / 2, n);
     }
@@ -89,6 +91,7 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
     if (ch_ok && bias) b2 = make_float2(bias[ch], bias[ch + 1]);
 
     __syncthreads();          // barrier init visible to all waiters
+    pdl_wait();               // also orders this kernel's output writes after the previous kernel's reads
     mbar_wait(bar, 0);
 
     const __half2* tile_in = reinterpret_cast<const __half2*>(smem);   // [IH][IW][16 pairs]
@@ -186,9 +189,10 @@ static int launch_dw(const void* x, const void* w, const float* bias, void* y, i
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dwconv)");
     const int tiles_x = (Wout + Cfg::TW - 1) / Cfg::TW, tiles_y = (Hout + Cfg::TH - 1) / Cfg::TH;
     dim3 grid(tiles_x * tiles_y, (C + DW_CB - 1) / DW_CB, N);
-    dwconv_kernel<K, S, PREC><<<grid, DW_THREADS, Cfg::SMEM, stream>>>(map, reinterpret_cast<const __half*>(w), bias,
-                                                                       reinterpret_cast<__half*>(y), C, Hout, Wout,
-                                                                       tiles_x, act);
+    cudaError_t le = launch_pdl(dwconv_kernel<K, S, PREC>, grid, dim3(DW_THREADS), (size_t)Cfg::SMEM, stream, map,
+                                reinterpret_cast<const __half*>(w), bias, reinterpret_cast<__half*>(y), C, Hout, Wout,
+                                tiles_x, act);
+    if (le != cudaSuccess) return cuda_fail(le, "launch dwconv_kernel");
     LP_LAUNCH_CHECK("dwconv_kernel");
     return LP_OK;
 }

@@ -105,10 +105,12 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     for (int i = threadIdx.x; i < p.n_tile; i += FP_THREADS) sBias[i] = p.b_pj ? p.b_pj[i] : 0.f;
     for (int i = threadIdx.x; i < p.nslabs * FP_CB; i += FP_THREADS)
         sBdw[i] = (p.b_dw && (HEAD || i < p.Ce)) ? p.b_dw[i] : 0.f;
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();                   // the expanded input of this block is complete from here on
 
     if (warp == FP_DW_WARPS) {
         // ------------------------------------------------------------------ TMA producer
@@ -399,7 +401,9 @@ extern "C" int lp_dw7_project_f16(const void* x, const void* w_dw, const float* 
                                          (int)FP_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dw7_project)");
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    dw_project_kernel<7, 0><<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(mx, mx, mw, md, p);
+    cudaError_t le = launch_pdl(dw_project_kernel<7, 0>, dim3(grid), dim3(FP_THREADS), FP_SMEM, (cudaStream_t)stream, mx, mx,
+                                mw, md, p);
+    if (le != cudaSuccess) return cuda_fail(le, "launch dw_project_kernel<7,0>");
     LP_LAUNCH_CHECK("dw_project_kernel<7,0>");
     return LP_OK;
 }
@@ -503,7 +507,9 @@ extern "C" int lp_head_fused_f16(const void* a1, const void* a2, const void* dw_
                                          (int)FP_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(head_fused)");
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    dw_project_kernel<5, 1><<<grid, FP_THREADS, FP_SMEM, (cudaStream_t)stream>>>(m0, m1, mw, md, p);
+    cudaError_t le = launch_pdl(dw_project_kernel<5, 1>, dim3(grid), dim3(FP_THREADS), FP_SMEM, (cudaStream_t)stream, m0, m1,
+                                mw, md, p);
+    if (le != cudaSuccess) return cuda_fail(le, "launch dw_project_kernel<5,1>");
     LP_LAUNCH_CHECK("dw_project_kernel<5,1>");
     return LP_OK;
 }

@@ -123,10 +123,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int nb = p.n_chunks * p.n_tile;
         for (int i = threadIdx.x; i < nb && i < MAX_BIAS; i += GEMM_THREADS) sBias[i] = p.bias ? p.bias[i] : 0.f;
     }
+    pdl_launch_dependents();      // the next kernel may start its own prologue
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();                   // activations written by the previous kernel are complete and visible from here on
 
     // Work distribution.  Streaming mode: item t -> (m-tile t / n_chunks, chunk t %% n_chunks), strided over the grid.
     // Resident-weights mode (MODE_PW): the CTA keeps ONE N chunk for its whole life (its weights are loaded once),
@@ -466,7 +468,8 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
         grid = cpc * p.n_chunks;
     }
     if (grid < 1) return LP_OK;
-    gemm_tc_kernel<MODE><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(a0, a1, b, mo, mr, p);
+    cudaError_t le = launch_pdl(gemm_tc_kernel<MODE>, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM, stream, a0, a1, b, mo, mr, p);
+    if (le != cudaSuccess) return cuda_fail(le, "launch gemm_tc_kernel");
     LP_LAUNCH_CHECK("gemm_tc_kernel");
     return LP_OK;
 }
