@@ -120,14 +120,14 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
                 for (int s = 0; s < p.nslabs; ++s) {
                     if ((s & 1) == 0) {   // projection weights of K block s/2
-                        mbar_wait(&bars->b_empty[bs], bph ^ 1);
+                        mbar_wait_backoff(&bars->b_empty[bs], bph ^ 1);
                         mbar_expect_tx(&bars->b_full[bs], p.n_tile * 128);
                         tma_load_2d(sB + bs * FP_B_BYTES, &map_w, &bars->b_full[bs], 0, (s >> 1) * p.n_tile);
                         if (++bs == FP_NB) { bs = 0; bph ^= 1; }
                     }
                     const int g = s & 1;                              // even / odd slab group, stages g and g+2
                     const uint32_t is = 2 * (iu[g] & 1) + g;
-                    mbar_wait(&bars->in_empty[is], ((iu[g] >> 1) & 1) ^ 1);
+                    mbar_wait_backoff(&bars->in_empty[is], ((iu[g] >> 1) & 1) ^ 1);
                     mbar_expect_tx(&bars->in_full[is], Cfg::IN_BYTES + Cfg::W_BYTES);
                     const bool second = HEAD && s >= p.ns0;
                     tma_load_4d(sIn + is * FP_IN_STRIDE, second ? &map_x1 : &map_x, &bars->in_full[is],
@@ -144,11 +144,11 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             uint32_t bs = 0, bph = 0, kbc = 0;
             int it = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-                mbar_wait(&bars->tmem_empty, (it & 1) ^ 1);
+                mbar_wait_backoff(&bars->tmem_empty, (it & 1) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
-                    mbar_wait(&bars->a_full, kbc & 1);
-                    mbar_wait(&bars->b_full[bs], bph);
+                    mbar_wait_backoff(&bars->a_full, kbc & 1);
+                    mbar_wait_backoff(&bars->b_full[bs], bph);
                     tc_fence_after();
                     const int k16 = 2 * min(2, p.nslabs - 2 * kb);      // 32 channels per slab present in this K block
                     const uint32_t b_base = smem_u32(sB + bs * FP_B_BYTES);
