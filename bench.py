@@ -255,6 +255,75 @@ def time_fused_kernel(n, ce, co, hw, device):
     return t, alg, flops
 
 
+def time_deconv_kernel(n, cr, cw, co, hw, device):
+    """Fusion-deconv level (both ConvT branches + bias + ReLU) at the largest level of the workload."""
+    import numpy as np
+    import torch
+    from litepose_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(0)
+    wr = (rs.randn(cr, co, 4, 4) * 0.05).astype(np.float16).view(np.uint16)
+    ww = (rs.randn(cw, co, 4, 4) * 0.05).astype(np.float16).view(np.uint16)
+    wpk = np.zeros(lib.lp_deconv_packed_elems(cr, cw, co), np.uint16)
+    bpk = np.zeros(lib.lp_deconv_packed_bias_elems(co), np.float32)
+    _lib.check(lib.lp_deconv_pack(wr.ctypes.data, ww.ctypes.data, None, cr, cw, co, wpk.ctypes.data, bpk.ctypes.data))
+    wpd = torch.from_numpy(wpk).view(torch.float16).to(device)
+    bpd = torch.from_numpy(bpk).to(device)
+    a = torch.randn((n, hw, hw, cr), device=device).half()
+    b = torch.randn((n, hw, hw, cw), device=device).half()
+    out = torch.empty((n, 2 * hw, 2 * hw, co), dtype=torch.float16, device=device)
+    s = torch.cuda.current_stream().cuda_stream
+    t = _time_kernel(lambda: _lib.check(lib.lp_fusion_deconv_f16(a.data_ptr(), b.data_ptr(), wpd.data_ptr(), bpd.data_ptr(),
+                                                                 out.data_ptr(), n, hw, hw, cr, cw, co, s)), device)
+    alg = 2 * (n * hw * hw * (cr + cw) + n * 4 * hw * hw * co + 16 * co * (cr + cw)) + 4 * co
+    return t, alg
+
+
+def time_forward_only(model, pipe, x_dev, device, iters=5):
+    """Forward-only comparison on the same device: the hand-written engine (plain + mirrored pass, as in the step)
+    against the SAME nn.Module graph executed by stock PyTorch eager ops (cuDNN fp16, cudnn.benchmark) - the op
+    sequence of the reference's pose_mobilenet.py.  Informational: the stock reference itself is not on this box."""
+    import copy
+    import torch
+    eng = pipe.engine
+
+    def ours():
+        eng.run(x_dev, flip=False, out_fp32=True, clone=False)
+        eng.run(x_dev, flip=True, out_fp32=True, clone=False)
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / n
+
+    t_ours = timed(ours, iters)
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        eager = copy.deepcopy(model).half().eval()
+        xh = x_dev.half()
+
+        def stock():
+            with torch.no_grad():
+                o = eager._forward_modules(xh)
+                f = eager._forward_modules(torch.flip(xh, [3]))
+                return [t.float() for t in o + f]
+
+        t_eager = timed(stock, iters)
+        del eager
+    finally:
+        torch.backends.cudnn.benchmark = old
+    torch.cuda.empty_cache()
+    return t_ours, t_eager
+
+
 # ------------------------------------------------------------------------------ main arm
 def main():
     args = parse_args()
@@ -417,6 +486,27 @@ def main():
                                           "achieved": alg / t_k / 1e9, "frac": alg / t_k / 1e9 / peak_gbs,
                                           "algorithmic_bytes": alg, "avg_launch_us": t_k * 1e6}}
 
+    ds = arch["deconv_setting"]
+    cr_l2, cw_l2 = ds[-2], arch["backbone_setting"][0]["channel"]
+    try:
+        t_d, alg_d = time_deconv_kernel(B, cr_l2, cw_l2, ds[-1], S // 4, dev)
+        roofline["fusion_deconv_kernel"] = {
+            "kernel": "fusion deconv level %d: %dx%dx%dx(%d+%d)->%d" % (len(ds) - 1, B, S // 4, S // 4, cr_l2, cw_l2, ds[-1]),
+            "achieved": alg_d / t_d / 1e9, "frac": alg_d / t_d / 1e9 / peak_gbs, "algorithmic_bytes": alg_d,
+            "avg_launch_us": t_d * 1e6}
+    except Exception as e:   # never lose the bench line over the auxiliary entry
+        roofline["fusion_deconv_kernel"] = {"error": str(e)[:200]}
+
+    fwd = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            t_ours, t_eager = time_forward_only(model, pipe, x_dev, dev)
+            fwd = {"ours_fps": B / t_ours, "torch_eager_fp16_fps": B / t_eager, "ratio": t_eager / t_ours,
+                   "what": "forward only, plain + mirrored pass per frame, batch %d; torch_eager = the same nn.Module "
+                           "graph on stock PyTorch ops (cuDNN fp16, benchmark mode), not the reference checkout" % B}
+        except Exception as e:
+            fwd = {"error": str(e)[:200]}
+
     # ---- CPU baseline (oracle port) on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -445,7 +535,7 @@ def main():
         "gpu_launches": launches_per_step * args.steps * 2 * world,
         "launches_per_step": launches_per_step,
         "cuda_graphs": not args.no_graphs,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "forward_only": fwd,
         "persons_found_rank0": found[:8],
     }
     print(json.dumps(line), flush=True)

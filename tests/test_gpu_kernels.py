@@ -17,11 +17,12 @@ def test_library_and_device():
     _lib.check(lib.lp_device_check(), "device")
 
 
-@pytest.mark.parametrize("fp32_in,flip", [(True, False), (False, False), (True, True)])
-def test_stem(fp32_in, flip):
+@pytest.mark.parametrize("h,w", [(64, 96), (32, 320), (20, 36), (16, 132)])   # vector path / >1 CTA column / generic path
+@pytest.mark.parametrize("fp32_in,flip", [(True, False), (False, False), (True, True), (False, True)])
+def test_stem(fp32_in, flip, h, w):
     lib = _lib.load()
     g = torch.Generator().manual_seed(0)
-    n, h, w = 2, 64, 96
+    n = 2
     x = torch.randn(n, 3, h, w, generator=g)
     wt = q16(torch.randn(32, 3, 3, 3, generator=g) * 0.3)
     b = torch.randn(32, generator=g) * 0.1
