@@ -171,6 +171,30 @@ int lp_adjust_refine_f32(const float* det, const float* tag, int N, int J, int H
                          int do_adjust, int do_refine, void* workspace, size_t workspace_bytes,
                          lp_stream_t stream);
 
+/* ---- fast_utils plugin on the GPU ("next" row 2) -------------------------------
+ * The reference's own native grouping for its "fast inference" demo parser
+ * (nano_demo/fast_utils/group.py:38-47), batched over N images.
+ *
+ * lp_find_peaks_f32 replaces find_peaks_out_nchw (nano_demo/fast_utils/parse/find_peaks.cpp:80-97,
+ * bound by plugins.cpp:9-29): per (image, joint) plane the first M pixels in scan order with
+ * value >= threshold and no strictly larger value in the window_size x window_size
+ * neighbourhood.  input, tmap [N,C,H,W] f32; count [N,C] i32, val/tag [N,C,M] f32,
+ * ind [N,C,M,2] i32 = (x, y).  Entries past count are left untouched (the reference's
+ * allocate-and-return variant zero-fills first, plugins.cpp:52-56).
+ *
+ * lp_assign_f32 replaces assign_out (assign.cpp:68-122, bound by plugins.cpp:66-82) for every
+ * image: persons are built joint by joint in joint_order (i32 [C]) with the reference's
+ * slack-array KM (assign.cpp:15-66), same float arithmetic and visiting order.
+ * ans [N,M,C,4] f32 = (x, y, val, tag), untouched where nothing is assigned;
+ * num_person [N] i32; status [N] i32: 0, or 1 when KM hit the round cap (the reference has no
+ * cap and would not return).  M <= 32 (LP_ERR_CAPACITY above; the reference's arrays hold 10). */
+int lp_find_peaks_f32(const float* input, const float* tmap, int N, int C, int H, int W, int M,
+                      float threshold, int window_size, int32_t* count, float* val, float* tag,
+                      int32_t* ind, lp_stream_t stream);
+int lp_assign_f32(const int32_t* count, const float* val, const float* tag, const int32_t* ind,
+                  const int32_t* joint_order, int N, int C, int M, float threshold,
+                  int32_t* num_person, float* ans, int32_t* status, lp_stream_t stream);
+
 /* ---- glue ("next" row 1): fused flip/upsample/average/project ----------------
  * From the two forward passes' outputs (plain: o0 [N,2J,h,w], o1 [N,J,2h,2w]; flipped
  * pass: f0, f1, NULL when flip == 0) produce det [N,J,Hd,Wd] and tag [N,J,Hd,Wd,T]

@@ -25,7 +25,7 @@ class LitePoseError(RuntimeError):
 
 
 _c = ctypes
-_vp, _i, _sz, _d = _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_double
+_vp, _i, _sz, _d, _f = _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_double, _c.c_float
 
 # name -> (restype, argtypes); every symbol declared in include/litepose_b200.h
 SIGNATURES = {
@@ -61,6 +61,8 @@ SIGNATURES = {
     "lp_adjust_refine_workspace_bytes": (_sz, [_i, _i, _i]),
     "lp_adjust_refine_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "lp_glue_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lp_find_peaks_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "lp_assign_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
 }
 
 _lock = threading.Lock()

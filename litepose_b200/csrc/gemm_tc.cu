@@ -580,6 +580,17 @@ extern "C" int lp_pw1x1_f16(const void* a, const void* w_packed, const float* bi
 }
 
 // ------------------------------------------------------------------ fusion deconv
+// Two kernels share one packed-weight buffer: [tiled-kernel weights | row-kernel weights (when the channels qualify)].
+// Wide maps run the row-streaming kernel (deconv_rows.cu), the others the tiled MODE_DECONV kernel above.
+namespace lp {
+bool deconv_rows_channels_ok(int Cr, int Cw, int Co);
+bool deconv_rows_shape_ok(int W);
+size_t deconv_rows_packed_elems(int Cr, int Cw, int Co);
+void deconv_rows_pack(const uint16_t* wr, const uint16_t* ww, int Cr, int Cw, int Co, uint16_t* wp);
+int launch_deconv_rows(const void* refined, const void* raw, const void* w_rows, const float* bias_packed, void* out, int N,
+                       int H, int W, int Cr, int Cw, int Co, cudaStream_t stream);
+}  // namespace lp
+
 static int deconv_ntile(int Co) { return round_up(Co, 16); }
 
 // enumerate steps; optionally emit packed weights
@@ -639,7 +650,7 @@ static int deconv_program(int Cr, int Cw, int Co, Step* steps, int* total_bt, co
 extern "C" size_t lp_deconv_packed_elems(int Cr, int Cw, int Co) {
     int bt = 0;
     if (deconv_program(Cr, Cw, Co, nullptr, &bt, nullptr, nullptr, nullptr) < 0) return 0;
-    return (size_t)bt * deconv_ntile(Co) * BK;
+    return (size_t)bt * deconv_ntile(Co) * BK + deconv_rows_packed_elems(Cr, Cw, Co);
 }
 extern "C" size_t lp_deconv_packed_bias_elems(int Co) { return (size_t)deconv_ntile(Co); }
 extern "C" int lp_deconv_pack(const uint16_t* wr, const uint16_t* ww, const float* bias, int Cr, int Cw, int Co,
@@ -648,6 +659,7 @@ extern "C" int lp_deconv_pack(const uint16_t* wr, const uint16_t* ww, const floa
     LP_CHECK_ARG(Cr % 8 == 0 && Cw % 8 == 0 && Co % 8 == 0 && Co <= 64, "lp_deconv_pack: bad channels %d %d %d", Cr, Cw, Co);
     int bt = 0;
     LP_CHECK_ARG(deconv_program(Cr, Cw, Co, nullptr, &bt, wr, ww, wp) > 0, "lp_deconv_pack: too many K blocks");
+    if (deconv_rows_channels_ok(Cr, Cw, Co)) deconv_rows_pack(wr, ww, Cr, Cw, Co, wp + (size_t)bt * deconv_ntile(Co) * BK);
     for (int i = 0; i < deconv_ntile(Co); ++i) bp[i] = (bias && i < Co) ? bias[i] : 0.f;
     return LP_OK;
 }
@@ -663,6 +675,15 @@ extern "C" int lp_fusion_deconv_f16(const void* refined, const void* raw, const 
     p.n_tile = deconv_ntile(Co);
     p.num_steps = deconv_program(Cr, Cw, Co, p.steps, &p.total_bt, nullptr, nullptr, nullptr);
     LP_CHECK_ARG(p.num_steps > 0, "lp_fusion_deconv_f16: too many K blocks");
+    if ((reinterpret_cast<uintptr_t>(refined) | reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(out) |
+         reinterpret_cast<uintptr_t>(w_packed)) & 15) {
+        set_error("lp_fusion_deconv_f16: pointers must be 16-byte aligned");
+        return LP_ERR_ALIGN;
+    }
+    if (deconv_rows_channels_ok(Cr, Cw, Co) && deconv_rows_shape_ok(W)) {
+        const uint16_t* w_rows = reinterpret_cast<const uint16_t*>(w_packed) + (size_t)p.total_bt * p.n_tile * BK;
+        return launch_deconv_rows(refined, raw, w_rows, bias_packed, out, N, H, W, Cr, Cw, Co, (cudaStream_t)stream);
+    }
     pick_spatial_tile(H, W, &p.TH, &p.TW);
     p.tiles_x = (W + p.TW - 1) / p.TW;
     p.tiles_y = (H + p.TH - 1) / p.TH;

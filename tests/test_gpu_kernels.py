@@ -93,6 +93,9 @@ def test_pw1x1(m, k, n, act, res):
 @pytest.mark.parametrize("n,h,w,cr,cw,co", [
     (2, 16, 16, 80, 48, 16), (1, 32, 32, 120, 48, 32), (2, 20, 12, 160, 96, 64), (1, 64, 64, 24, 16, 32),
     (1, 28, 28, 32, 32, 24), (3, 8, 8, 16, 24, 24),
+    # wide maps: row-streaming kernel (strips of 128 px; partial strips; odd chunk counts; long per-CTA row chains)
+    (2, 8, 128, 24, 16, 32), (1, 5, 160, 24, 16, 32), (2, 12, 96, 32, 32, 24), (1, 7, 128, 16, 8, 16),
+    (2, 3, 256, 8, 8, 8), (8, 128, 128, 24, 16, 32), (1, 1, 128, 40, 24, 40),
 ])
 def test_fusion_deconv(n, h, w, cr, cw, co):
     lib = _lib.load()
