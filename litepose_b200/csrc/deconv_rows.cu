@@ -96,6 +96,23 @@ struct DrCursor {
     }
 };
 
+// all MMAs of one tile (10 groups x K16 slices), fully unrolled; *_lo are shared-memory addresses >> 4
+template <int K16>
+__device__ __forceinline__ void dr_issue_tile(uint64_t desc_hi, const uint32_t (&slot_lo)[3], uint32_t w_lo, uint32_t dbase,
+                                              uint32_t nt, const uint32_t (&idesc)[5]) {
+#pragma unroll
+    for (int g = 0; g < DR_G; ++g) {
+        const uint32_t a_lo = slot_lo[dr_g_dy(g) + 1] + (dr_g_dx(g) + 1) * 8;   // (dx+1) pixel rows of 128 B
+        const uint32_t b_lo = w_lo + dr_g_bt(g) * nt * 8;
+        const uint32_t d = dbase + dr_g_pos(g) * nt;
+        const uint32_t id = idesc[dr_g_len(g)];
+#pragma unroll
+        for (int k = 0; k < K16; ++k)
+            tc_mma_f16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), id,
+                       (g > 0 || k > 0) ? 1u : 0u);
+    }
+}
+
 __global__ void __launch_bounds__(DR_THREADS, 1)
 deconv_rows_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ DrParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -225,15 +242,11 @@ deconv_rows_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
 #pragma unroll
                 for (int d = 0; d < 3; ++d) slot_lo[d] = slot0_lo + (uint32_t)((base + d) % DR_NS) * (DR_SLOT_BYTES >> 4);
                 const uint32_t dbase = tmem_base + buf * 4 * nt;
-#pragma unroll
-                for (int g = 0; g < DR_G; ++g) {
-                    const uint32_t a_lo = slot_lo[dr_g_dy(g) + 1] + (dr_g_dx(g) + 1) * 8;   // (dx+1) pixel rows of 128 B
-                    const uint32_t b_lo = w_lo + dr_g_bt(g) * nt * 8;
-                    const uint32_t d = dbase + dr_g_pos(g) * nt;
-                    const uint32_t id = idesc[dr_g_len(g)];
-                    for (int k = 0; k < k16; ++k)
-                        tc_mma_f16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), id,
-                                   (g > 0 || k > 0) ? 1u : 0u);
+                switch (k16) {
+                    case 1: dr_issue_tile<1>(desc_hi, slot_lo, w_lo, dbase, nt, idesc); break;
+                    case 2: dr_issue_tile<2>(desc_hi, slot_lo, w_lo, dbase, nt, idesc); break;
+                    case 3: dr_issue_tile<3>(desc_hi, slot_lo, w_lo, dbase, nt, idesc); break;
+                    default: dr_issue_tile<4>(desc_hi, slot_lo, w_lo, dbase, nt, idesc); break;
                 }
                 // rows no later tile needs go back to the producers once these MMAs retire
                 tc_commit(&bars->empty[base % DR_NS]);
@@ -261,27 +274,35 @@ deconv_rows_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
             mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 4 * p.n_tile;
-            uint32_t r[16];
+            for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
+                // the four phases' accumulators of this 16-column group: issue all TMEM loads, wait once
+                uint32_t r[4][16];
 #pragma unroll
-            for (int pos = 0; pos < 4; ++pos) {
-                const int a = dr_pos_a(pos), b = dr_pos_b(pos);
-                uint8_t* dst = st + a * (DR_TW * p.pair_pitch) + row * p.pair_pitch + b * (Co * 2);
-                for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
-                    tc_ld16(taddr + pos * p.n_tile + c0, r);
-                    tc_wait_ld();
-                    if (c0 < Co) {
+                for (int pos = 0; pos < 4; ++pos) tc_ld16(taddr + pos * p.n_tile + c0, r[pos]);
+                float bv[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + 4 * i);
+                    bv[4 * i] = b4.x; bv[4 * i + 1] = b4.y; bv[4 * i + 2] = b4.z; bv[4 * i + 3] = b4.w;
+                }
+                tc_wait_ld();
+                if (c0 < Co) {
+#pragma unroll
+                    for (int pos = 0; pos < 4; ++pos) {
+                        const int a = dr_pos_a(pos), b = dr_pos_b(pos);
+                        uint8_t* dst = st + a * (DR_TW * p.pair_pitch) + row * p.pair_pitch + b * (Co * 2) + c0 * 2;
                         uint4 o0, o1;
                         __half2* h0 = reinterpret_cast<__half2*>(&o0);
                         __half2* h1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            h0[i] = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * i]) + sBias[c0 + 2 * i], 0.f),
-                                                      fmaxf(__uint_as_float(r[2 * i + 1]) + sBias[c0 + 2 * i + 1], 0.f));
-                            h1[i] = __floats2half2_rn(fmaxf(__uint_as_float(r[8 + 2 * i]) + sBias[c0 + 8 + 2 * i], 0.f),
-                                                      fmaxf(__uint_as_float(r[8 + 2 * i + 1]) + sBias[c0 + 8 + 2 * i + 1], 0.f));
+                            h0[i] = __floats2half2_rn(fmaxf(__uint_as_float(r[pos][2 * i]) + bv[2 * i], 0.f),
+                                                      fmaxf(__uint_as_float(r[pos][2 * i + 1]) + bv[2 * i + 1], 0.f));
+                            h1[i] = __floats2half2_rn(fmaxf(__uint_as_float(r[pos][8 + 2 * i]) + bv[8 + 2 * i], 0.f),
+                                                      fmaxf(__uint_as_float(r[pos][8 + 2 * i + 1]) + bv[8 + 2 * i + 1], 0.f));
                         }
-                        *reinterpret_cast<uint4*>(dst + c0 * 2) = o0;
-                        if (c0 + 8 < Co) *reinterpret_cast<uint4*>(dst + c0 * 2 + 16) = o1;
+                        *reinterpret_cast<uint4*>(dst) = o0;
+                        if (c0 + 8 < Co) *reinterpret_cast<uint4*>(dst + 16) = o1;
                     }
                 }
             }
@@ -293,17 +314,26 @@ deconv_rows_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
             const int per_row = vw * cpp;
             uint4* orow0 = reinterpret_cast<uint4*>(p.out + (((size_t)n * 2 * p.H + 2 * y) * (2 * p.W) + 2 * x0) * Co);
             const size_t row_stride16 = ((size_t)2 * p.W * Co) >> 3;     // one output row in 16-byte units
+            // up to 1024 16-byte chunks per output row: all loads of a row first, then its stores
+#pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const uint8_t* srow = st + a * (DR_TW * p.pair_pitch);
                 uint4* orow = orow0 + a * row_stride16;
-                if (cpp == 8) {
-                    for (int i = et; i < per_row; i += DR_EPI_THREADS)
-                        orow[i] = *reinterpret_cast<const uint4*>(srow + (i >> 3) * p.pair_pitch + (i & 7) * 16);
-                } else {
-                    for (int i = et; i < per_row; i += DR_EPI_THREADS) {
-                        const int pair = i / cpp, c = i - pair * cpp;
-                        orow[i] = *reinterpret_cast<const uint4*>(srow + pair * p.pair_pitch + c * 16);
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = et + u * DR_EPI_THREADS;
+                    if (i < per_row) {
+                        int pair, c;
+                        if (cpp == 8) { pair = i >> 3; c = i & 7; }
+                        else { pair = i / cpp; c = i - pair * cpp; }
+                        v[u] = *reinterpret_cast<const uint4*>(srow + pair * p.pair_pitch + c * 16);
                     }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = et + u * DR_EPI_THREADS;
+                    if (i < per_row) orow[i] = v[u];
                 }
             }
             cur.next(p);

@@ -119,50 +119,75 @@ nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*windo
             const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(plane_thr + plane);
             thr = g > thr ? g : thr;
         }
-        for (int r = warp; r < rows; r += TK_WARPS) {
-            for (int x0 = 0; x0 < W; x0 += 32) {
-                const int x = x0 + lane;
-                const float thr_v = __uint_as_float((unsigned)(thr >> 32));      // 0 while no list is full
-                const float v = x < W ? s_val[(r + R) * W + x] : 0.f;
-                bool cand = v > 0.f && v >= thr_v;
-                if (__any_sync(0xffffffffu, cand)) {
-                    unsigned long long key = 0ull;
-                    if (cand) {
-                        // cheap reject first: most pixels lose against a direct neighbour
-                        const float* c = s_val + (r + R) * W + x;
-                        const float l = x > 0 ? c[-1] : NEG_INF, rr = x < W - 1 ? c[1] : NEG_INF;
-                        if (R > 0) cand = v >= l && v >= rr && v >= c[-W] && v >= c[W];
-                        if (cand) {
-                            float m = NEG_INF;
-                            const int xa = max(x - R, 0), xb = min(x + R, W - 1);
-                            for (int d = 0; d <= 2 * R; ++d)
-                                for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[(r + d) * W + xx]);
-                            if (v == m) {
-                                const unsigned idx = (unsigned)((y0 + r) * W + x);
-                                key = ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
-                            }
-                        }
-                    }
-                    unsigned bal = __ballot_sync(0xffffffffu, key > thr);
-                    if (bal) {
-                        while (bal) {
-                            const int src = __ffs(bal) - 1;
-                            bal &= bal - 1;
-                            const unsigned long long k2 = __shfl_sync(0xffffffffu, key, src);
-                            ntop = topk_insert(mytop, ntop, K, k2, lane);
-                        }
-                        if (ntop >= K) {
-                            const unsigned long long kth = mytop[K - 1];
-                            if (kth > thr) {
-                                if (lane == 0) atomicMax(&s_thr, kth);
-                                thr = kth;
-                            }
-                        }
-                    }
+        // Test of one pixel that passed the cheap value test: NMS window maximum, then the key (0 = no candidate).
+        auto pixel_key = [&](int r, int x, float v) -> unsigned long long {
+            const float* c = s_val + (r + R) * W + x;
+            // cheap reject first: most pixels lose against a direct neighbour
+            const float l = x > 0 ? c[-1] : NEG_INF, rr = x < W - 1 ? c[1] : NEG_INF;
+            if (R > 0 && !(v >= l && v >= rr && v >= c[-W] && v >= c[W])) return 0ull;
+            float m = NEG_INF;
+            const int xa = max(x - R, 0), xb = min(x + R, W - 1);
+            for (int d = 0; d <= 2 * R; ++d)
+                for (int xx = xa; xx <= xb; ++xx) m = fmaxf(m, s_val[(r + d) * W + xx]);
+            if (v != m) return 0ull;
+            const unsigned idx = (unsigned)((y0 + r) * W + x);
+            return ((unsigned long long)__float_as_uint(v) << 32) | (0xffffffffu - idx);
+        };
+        // Warp-wide insertion of the lanes' keys (ascending lane order) into this warp's list; refreshes the bound.
+        auto insert_keys = [&](unsigned long long key) {
+            unsigned bal = __ballot_sync(0xffffffffu, key > thr);
+            if (!bal) return;
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const unsigned long long k2 = __shfl_sync(0xffffffffu, key, src);
+                ntop = topk_insert(mytop, ntop, K, k2, lane);
+            }
+            if (ntop >= K) {
+                const unsigned long long kth = mytop[K - 1];
+                if (kth > thr) {
+                    if (lane == 0) atomicMax(&s_thr, kth);
+                    thr = kth;
                 }
-                // pick up the bound published by the other warps
-                const unsigned long long sh = *reinterpret_cast<volatile unsigned long long*>(&s_thr);
-                thr = sh > thr ? sh : thr;
+            }
+        };
+        for (int r = warp; r < rows; r += TK_WARPS) {
+            if (vec) {
+                // 4 pixels per lane (one 16-byte shared load), 128 per warp step; the slow path runs per sub-pixel
+                for (int x0 = 0; x0 < W; x0 += 128) {
+                    const int x = x0 + 4 * lane;
+                    const float thr_v = __uint_as_float((unsigned)(thr >> 32));      // 0 while no list is full
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (x < W) q = *reinterpret_cast<const float4*>(s_val + (r + R) * W + x);
+                    const float vv[4] = {q.x, q.y, q.z, q.w};
+                    bool c4[4];
+                    bool any4 = false;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        c4[u] = vv[u] > 0.f && vv[u] >= thr_v;
+                        any4 |= c4[u];
+                    }
+                    if (__any_sync(0xffffffffu, any4)) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (!__any_sync(0xffffffffu, c4[u])) continue;
+                            insert_keys(c4[u] ? pixel_key(r, x + u, vv[u]) : 0ull);
+                        }
+                    }
+                    // pick up the bound published by the other warps
+                    const unsigned long long sh = *reinterpret_cast<volatile unsigned long long*>(&s_thr);
+                    thr = sh > thr ? sh : thr;
+                }
+            } else {
+                for (int x0 = 0; x0 < W; x0 += 32) {
+                    const int x = x0 + lane;
+                    const float thr_v = __uint_as_float((unsigned)(thr >> 32));
+                    const float v = x < W ? s_val[(r + R) * W + x] : 0.f;
+                    const bool cand = v > 0.f && v >= thr_v;
+                    if (__any_sync(0xffffffffu, cand)) insert_keys(cand ? pixel_key(r, x, v) : 0ull);
+                    const unsigned long long sh = *reinterpret_cast<volatile unsigned long long*>(&s_thr);
+                    thr = sh > thr ? sh : thr;
+                }
             }
         }
         // publish this CTA's bound to the plane
