@@ -143,10 +143,15 @@ int lp_head_fused_f16(const void* a1, const void* a2, const void* dw_cat, const 
 /* ---- G1+G2: NMS (k x k window max, -inf padding) + top-K per (n,j) plane -----
  * det fp32 [N,J,H,W]; tag fp32 [N,J,H,W,T].  Order: value desc, flat index asc over
  * NMS survivors with value > 0; unused slots are (0.0f, index 0).
- * val_k [N,J,K] f32; ind_k [N,J,K] i32 (flat y*W+x); tag_k [N,J,K,T] f32.  K <= 64. */
+ * val_k [N,J,K] f32; ind_k [N,J,K] i32 (flat y*W+x); tag_k [N,J,K,T] f32.  K <= 64.
+ * min_value (double, compared as the reference does: float32 value widened to double): only survivors
+ * with value > max(min_value, 0) are reported.  0 reproduces top_k as the
+ * reference computes it; the full parse passes DETECTION_THRESHOLD, because match_by_tag drops every
+ * candidate with val <= DETECTION_THRESHOLD before it looks at anything else (group.py:43-45), so the
+ * keypoints are unchanged while background pixels never reach the NMS window test. */
 size_t lp_nms_topk_workspace_bytes(int N, int J, int H, int W, int K);
 int lp_nms_topk_f32(const float* det, const float* tag, int N, int J, int H, int W, int T,
-                    int nms_kernel, int K, float* val_k, int32_t* ind_k, float* tag_k,
+                    int nms_kernel, int K, double min_value, float* val_k, int32_t* ind_k, float* tag_k,
                     void* workspace, size_t workspace_bytes, lp_stream_t stream);
 
 /* ---- G3: tag matching (match_by_tag + Munkres), one image per CTA -----------

@@ -55,7 +55,7 @@ SIGNATURES = {
     "lp_head_fused_pack": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "lp_head_fused_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lp_nms_topk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "lp_nms_topk_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lp_nms_topk_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lp_tag_match_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "lp_tag_match_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _d, _d, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "lp_adjust_refine_workspace_bytes": (_sz, [_i, _i, _i]),

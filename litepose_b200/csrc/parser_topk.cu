@@ -8,6 +8,8 @@
 // plane keeps a running sorted top-K of 64-bit keys (value bits << 32 | ~index); the window maximum is
 // evaluated only for pixels that reach the current K-th value; candidates are compacted with warp
 // ballots and merged by one warp.  Kernel 2: one warp per plane merges the per-band lists and gathers tags.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace lp {
@@ -63,7 +65,7 @@ constexpr int TK_WARPS = TK_THREADS / 32;
 // K-th key -- so the k x k window maximum (the NMS test) is evaluated for a vanishing fraction of pixels and the
 // kernel streams at memory speed.  The per-warp lists are merged by topk_merge_kernel.
 __global__ void __launch_bounds__(TK_THREADS)
-nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*window radius*/, int SR, int K,
+nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*window radius*/, int SR, int K, float floor_v,
                       unsigned long long* __restrict__ partial, unsigned long long* __restrict__ plane_thr) {
     extern __shared__ __align__(16) float sm[];
     const int plane = blockIdx.y;
@@ -164,7 +166,7 @@ nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*windo
                     bool any4 = false;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        c4[u] = vv[u] > 0.f && vv[u] >= thr_v;
+                        c4[u] = vv[u] > floor_v && vv[u] >= thr_v;
                         any4 |= c4[u];
                     }
                     if (__any_sync(0xffffffffu, any4)) {
@@ -183,7 +185,7 @@ nms_topk_strip_kernel(const float* __restrict__ det, int H, int W, int R /*windo
                     const int x = x0 + lane;
                     const float thr_v = __uint_as_float((unsigned)(thr >> 32));
                     const float v = x < W ? s_val[(r + R) * W + x] : 0.f;
-                    const bool cand = v > 0.f && v >= thr_v;
+                    const bool cand = v > floor_v && v >= thr_v;
                     if (__any_sync(0xffffffffu, cand)) insert_keys(cand ? pixel_key(r, x, v) : 0ull);
                     const unsigned long long sh = *reinterpret_cast<volatile unsigned long long*>(&s_thr);
                     thr = sh > thr ? sh : thr;
@@ -256,7 +258,7 @@ extern "C" size_t lp_nms_topk_workspace_bytes(int N, int J, int H, int W, int K)
 }
 
 extern "C" int lp_nms_topk_f32(const float* det, const float* tag, int N, int J, int H, int W, int T, int nms_kernel,
-                               int K, float* val_k, int32_t* ind_k, float* tag_k, void* workspace,
+                               int K, double min_value, float* val_k, int32_t* ind_k, float* tag_k, void* workspace,
                                size_t workspace_bytes, lp_stream_t stream) {
     LP_CHECK_ARG(det && tag && val_k && ind_k && tag_k && workspace, "lp_nms_topk_f32: null pointer");
     LP_CHECK_ARG(N > 0 && J > 0 && H > 0 && W > 0 && T > 0 && (long long)H * W < (1ll << 31),
@@ -285,7 +287,14 @@ extern "C" int lp_nms_topk_f32(const float* det, const float* tag, int N, int J,
     unsigned long long* plane_thr = lists + (size_t)N * J * nstrips * TK_WARPS * K;
     cudaError_t em = cudaMemsetAsync(plane_thr, 0, (size_t)N * J * sizeof(unsigned long long), s);
     if (em != cudaSuccess) return cuda_fail(em, "cudaMemsetAsync(plane_thr)");
-    nms_topk_strip_kernel<<<grid, TK_THREADS, smem, s>>>(det, H, W, R, sr, K, lists, plane_thr);
+    // (double)v > min_value  <=>  v > floor_v with floor_v = min_value rounded DOWN to float (the reference compares the
+    // float32 values with a Python float, i.e. in double: group.py:43)
+    float floor_v = 0.f;
+    if (min_value > 0.0) {
+        floor_v = (float)min_value;
+        if ((double)floor_v > min_value) floor_v = nextafterf(floor_v, 0.f);
+    }
+    nms_topk_strip_kernel<<<grid, TK_THREADS, smem, s>>>(det, H, W, R, sr, K, floor_v, lists, plane_thr);
     LP_LAUNCH_CHECK("nms_topk_strip_kernel");
     topk_merge_kernel<<<N * J, 32, 0, s>>>(lists, tag, H * W, T, nstrips * TK_WARPS, K, val_k, ind_k, tag_k);
     LP_LAUNCH_CHECK("topk_merge_kernel");

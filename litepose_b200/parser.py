@@ -57,7 +57,9 @@ class DeviceParser(object):
         return b, self._jo[dev]
 
     # ---- stages (device tensors in, device tensors out; all on the current stream)
-    def top_k_device(self, det, tag):
+    def top_k_device(self, det, tag, min_value=0.0):
+        """min_value 0: the reference's top_k.  run() passes the detection threshold: match_by_tag discards
+        val <= DETECTION_THRESHOLD first (reference group.py:43-45), so the result of the parse is unchanged."""
         n, j, h, w = det.shape
         t = tag.shape[4]
         assert j == self.J and det.dtype == torch.float32 and tag.dtype == torch.float32
@@ -65,7 +67,7 @@ class DeviceParser(object):
         b, _ = self._buffers(det.device, n, h, w, t)
         s = torch.cuda.current_stream().cuda_stream
         _lib.check(self.lib.lp_nms_topk_f32(det.data_ptr(), tag.data_ptr(), n, j, h, w, t, self.nms_kernel, self.K,
-                                            b["val_k"].data_ptr(), b["ind_k"].data_ptr(), b["tag_k"].data_ptr(),
+                                            float(min_value), b["val_k"].data_ptr(), b["ind_k"].data_ptr(), b["tag_k"].data_ptr(),
                                             b["ws_topk"].data_ptr(), b["ws_topk"].numel(), s), "lp_nms_topk_f32")
         return b["val_k"], b["ind_k"], b["tag_k"]
 
@@ -81,7 +83,7 @@ class DeviceParser(object):
         with torch.cuda.device(det.device):
             b, jo = self._buffers(det.device, n, h, w, t)
             s = torch.cuda.current_stream().cuda_stream
-            self.top_k_device(det, tag)
+            self.top_k_device(det, tag, self.det_thr)
             _lib.check(self.lib.lp_tag_match_f32(
                 b["val_k"].data_ptr(), b["ind_k"].data_ptr(), b["tag_k"].data_ptr(), n, j, self.K, t, w,
                 jo.data_ptr(), self.det_thr, self.tag_thr, self.use_det_val, self.ignore_too_much, self.K,

@@ -163,6 +163,10 @@ def test_error_codes():
     (2, 32, 32, 96, 16, True), (1, 16, 16, 96, 16, False), (2, 48, 32, 192, 32, True), (1, 32, 32, 288, 48, True),
     (1, 32, 32, 720, 120, True), (2, 16, 16, 144, 24, True), (1, 20, 40, 432, 72, False), (1, 32, 32, 288, 120, False),
     (3, 64, 64, 96, 16, True),
+    # more tiles than SMs: several tiles per persistent CTA (operand / accumulator double buffering, alternating slab
+    # groups for odd slab counts, deferred epilogue, single-buffer weight ring for wide projections)
+    (8, 128, 128, 96, 16, True), (5, 96, 112, 160, 32, True), (36, 32, 32, 288, 48, True), (24, 48, 48, 720, 120, True),
+    (20, 48, 48, 48, 8, False), (6, 80, 80, 32, 16, True), (1, 16, 16, 960, 160, True),
 ])
 def test_dw7_project_fused(n, h, w, ce, co, res):
     """fused depthwise-7x7 + projection (+residual) against the unfused fp32 reference"""
@@ -193,6 +197,7 @@ def test_dw7_project_fused(n, h, w, ce, co, res):
 @pytest.mark.parametrize("n,h,w,c1,c2,co,fp32", [
     (2, 32, 32, 24, 16, 28, True), (1, 64, 64, 32, 16, 14, True), (1, 48, 16, 40, 24, 28, False),
     (2, 16, 16, 64, 24, 34, True), (1, 20, 36, 24, 16, 28, True),
+    (4, 144, 160, 32, 16, 14, True), (6, 96, 96, 24, 16, 28, True), (5, 80, 96, 40, 24, 28, False),     # many tiles per CTA
 ])
 def test_head_fused(n, h, w, c1, c2, co, fp32):
     """both SepConv2d heads of a level (dw5+BN+ReLU -> 1x1, two branches summed) in one kernel"""

@@ -80,6 +80,39 @@ def test_topk_plateau_and_empty():
     assert (top["val_k"][0, 2:] == 0).all()
 
 
+def test_detection_threshold_prefilter_is_exact():
+    """parse() hands DETECTION_THRESHOLD to the NMS/top-K kernel (match_by_tag drops val <= threshold first,
+    reference group.py:43-45).  The compare must be the reference's: float32 value widened to double against the
+    Python float - peaks sitting exactly on float32(0.1) (> 0.1 in double) and one ulp below it pin the edge."""
+    cfg = get_cfg(input_size=256)
+    thr = cfg.TEST.DETECTION_THRESHOLD
+    f = np.float32(thr)
+    assert float(f) > thr                                  # float32(0.1) lies above the double 0.1
+    below = np.nextafter(f, np.float32(0))
+    rs = np.random.RandomState(3)
+    det = (rs.rand(2, 14, 40, 48) * 0.05).astype(np.float32)
+    tag = rs.randn(2, 14, 40, 48, 2).astype(np.float32)
+    for n in range(2):
+        for j in range(14):
+            det[n, j, 8, 9] = f                            # kept by the reference (0.10000000149 > 0.1)
+            det[n, j, 20, 30] = below                      # dropped
+            det[n, j, 30, 12] = np.float32(0.6)
+            tag[n, j, 8, 9] = 1.0
+            tag[n, j, 30, 12] = 5.0
+    p = _parser(cfg)
+    dd, td = torch.from_numpy(det).cuda(), torch.from_numpy(tag).cuda()
+    got = p.parse_batch(dd, td, True, True)
+    exp = group_ref.HeatmapParser(cfg).parse_batch(det.copy(), tag.copy(), True, True)
+    for g, e in zip(got, exp):
+        a = np.asarray(g[0][0], np.float32).reshape(-1, 14, 5)
+        b = np.asarray(e[0][0], np.float32).reshape(-1, 14, 5)
+        assert a.shape == b.shape and np.array_equal(a, b)
+        assert (b[:, :, 2] == f).any() and not (b[:, :, 2] == below).any()
+    val_k, ind_k, _ = p.device_parser.top_k_device(dd, td, thr)
+    v = val_k.cpu().numpy()
+    assert ((v > 0).sum(axis=2) == 2).all() and (v[:, :, 1] == f).all()
+
+
 @pytest.mark.parametrize("flip,proj", [(1, 1), (0, 1), (1, 0)])
 def test_glue_golden(golden_dir, flip, proj):
     lib = _lib.load()
