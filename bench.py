@@ -324,6 +324,66 @@ def time_forward_only(model, pipe, x_dev, device, iters=5):
     return t_ours, t_eager
 
 
+def time_variants(args, model, x_dev, plant, device, iters=5):
+    """(a) the reference's nano-demo settings on the same frames: FLIP_TEST / ADJUST / REFINE off (nano_demo/core/__init__.py
+    :106-116), full parser; (b) the fast_utils parser (find_peaks + KM assign, nano_demo/fast_utils/group.py:38-47) on the
+    projected maps of the step: GPU plugin (whole batch) vs the C restatement of the reference's native code on one host
+    core (per frame; the reference's own loop is per frame)."""
+    import time as _t
+    import numpy as np
+    import torch
+    from litepose_b200.config import get_cfg
+    from litepose_b200.fast_utils.group import HeatmapParser as FastParser
+    from litepose_b200.pipeline import LitePosePipeline, PlantedCrowd
+    B, S = x_dev.shape[0], args.size
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / n
+
+    out = {}
+    cfg_fast = get_cfg(input_size=S, flip_test=False, adjust=False, refine=False)
+    pipe_fast = LitePosePipeline(model, cfg_fast, use_graphs=True)
+    plant1 = PlantedCrowd(B, 14, S, S, 1, num_people=args.people, seed=77, device=device)
+    t = timed(lambda: pipe_fast.step_device(x_dev, plant1), iters)
+    out["nano_demo_settings"] = {"frames_per_s": B / t, "ms_per_step": t * 1e3,
+                                 "what": "FLIP_TEST/ADJUST/REFINE off, otherwise the bench workload (device resident)"}
+    # fast_utils parser on the projected maps of that step
+    st = pipe_fast._get_state(B, S, S, x_dev.dtype, plant1)
+    det, tag = st["det"].clone(), st["tag"].clone()
+    fp = FastParser(cfg_fast)
+    tg = timed(lambda: fp.parse_batch(det, tag), iters)
+    num, _ = fp.parse_batch(det, tag)
+    fast = {"gpu_frames_per_s": B / tg, "gpu_ms_per_batch": tg * 1e3, "persons_found": num[:8].tolist(),
+            "what": "find_peaks + KM assign on %d projected maps %dx%dx%dx%d" % (B, B, 14, S, S)}
+    try:
+        from oracle import fast_utils_ref as fu
+        d, tm = det[:2].cpu().numpy(), tag[:2, :, :, :, 0].cpu().numpy()
+        params = dict(detection_threshold=fp.params.detection_threshold, window_size=fp.params.window_size,
+                      max_num_people=fp.params.max_num_people, tag_threshold=fp.params.tag_threshold,
+                      joint_order=[j for j in fp.params.joint_order if j < 14][:14])
+        fu.parse(d, tm, params, "port")
+        t0 = _t.perf_counter()
+        fu.parse(d, tm, params, "port")
+        dt = _t.perf_counter() - t0
+        fast["cpu_port_frames_per_s"] = 2 / dt
+        fast["cpu_port_cores"] = 1
+    except Exception as e:
+        fast["cpu_port_error"] = str(e)[:120]
+    out["fast_utils_parser"] = fast
+    del pipe_fast
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------ main arm
 def main():
     args = parse_args()
@@ -507,6 +567,14 @@ def main():
         except Exception as e:
             fwd = {"error": str(e)[:200]}
 
+    # ---- secondary variants (N=1 only, short): the nano-demo "fast" settings and the fast_utils parser (8(d), 8(f) row 2)
+    variants = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            variants = time_variants(args, model, x_dev, plant, dev)
+        except Exception as e:
+            variants = {"error": str(e)[:200]}
+
     # ---- CPU baseline (oracle port) on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -535,7 +603,7 @@ def main():
         "gpu_launches": launches_per_step * args.steps * 2 * world,
         "launches_per_step": launches_per_step,
         "cuda_graphs": not args.no_graphs,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "forward_only": fwd,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "forward_only": fwd, "variants": variants,
         "persons_found_rank0": found[:8],
     }
     print(json.dumps(line), flush=True)
