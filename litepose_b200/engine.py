@@ -36,20 +36,98 @@ class _Op(object):
         self.name, self.fn, self.args = name, fn, args
 
 
+FOLDED_FORMAT = "litepose_b200-folded-1"
+
+
 class LitePoseEngine(object):
     def __init__(self, state_dict, arch, device, num_joints_out=None):
+        self._init_common(arch, device)
+        sd = {k: v.detach() for k, v in state_dict.items()}
+        self._prep(sd)
+
+    def _init_common(self, arch, device):
+        """device 'cpu' is accepted for weight preparation / folded-checkpoint conversion only: run() needs CUDA."""
         self.lib = _lib.load()
         self.device = torch.device(device)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.lp_device_check(), "lp_device_check")
+        if self.device.type == "cuda":
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.lp_device_check(), "lp_device_check")
         self.arch = arch
         self.plans = {}
         self.use_graphs = False
         import os
         self.fuse_dw_project = os.environ.get("LP_FUSE_DW_PROJECT", "1") != "0"
         self.fuse_heads = os.environ.get("LP_FUSE_HEADS", "1") != "0"
-        sd = {k: v.detach() for k, v in state_dict.items()}
-        self._prep(sd)
+
+    # ------------------------------------------------------------------ folded checkpoint ("next" row 4)
+    # BN fold (reference fuse_bn.py:81-162) and kernel packing become a load-time no-op: the file holds exactly the
+    # arrays the kernels read (fp16 packed weights, fp32 biases) plus the shape metadata of the plan builder.
+    def export_folded(self, path):
+        import json
+        arrays, meta = {}, {}
+
+        def walk(node, prefix):
+            if isinstance(node, dict):
+                for k, v in node.items():
+                    walk(v, prefix + [str(k)])
+            elif isinstance(node, list):
+                meta["/".join(prefix) + "#len"] = len(node)
+                for i, v in enumerate(node):
+                    walk(v, prefix + [str(i)])
+            elif torch.is_tensor(node):
+                arrays["/".join(prefix)] = node.detach().cpu().numpy()
+            else:
+                meta["/".join(prefix)] = node
+
+        walk(self.P, [])
+        header = {"format": FOLDED_FORMAT, "arch": self.arch, "channels": self.channels, "meta": meta,
+                  "lib_version": int(self.lib.lp_version())}
+        np.savez(path, __header__=np.frombuffer(json.dumps(header).encode(), dtype=np.uint8), **arrays)
+
+    @classmethod
+    def from_folded(cls, path, device):
+        import json
+        z = np.load(path)
+        header = json.loads(bytes(z["__header__"]).decode())
+        if header.get("format") != FOLDED_FORMAT:
+            raise ValueError("not a %s file: %r" % (FOLDED_FORMAT, header.get("format")))
+        eng = cls.__new__(cls)
+        eng._init_common(header["arch"], device)
+        if header["lib_version"] != int(eng.lib.lp_version()):
+            raise ValueError("folded checkpoint was packed for library version %d, this is %d (re-export it)"
+                             % (header["lib_version"], int(eng.lib.lp_version())))
+        eng.channels = list(header["channels"])
+        meta = header["meta"]
+        root = {}
+
+        def put(keys, value):
+            node = root
+            for k in keys[:-1]:
+                node = node.setdefault(k, {})
+            node[keys[-1]] = value
+
+        for k in z.files:
+            if k != "__header__":
+                put(k.split("/"), torch.from_numpy(np.ascontiguousarray(z[k])).to(eng.device))
+        lists = set()
+        for k, v in meta.items():
+            if k.endswith("#len"):
+                lists.add(k[:-4])
+            else:
+                put(k.split("/"), v)
+
+        def fix(node, prefix):
+            if isinstance(node, dict):
+                for k in list(node.keys()):
+                    node[k] = fix(node[k], prefix + [k])
+                if "/".join(prefix) in lists:
+                    return [node[str(i)] for i in range(meta["/".join(prefix) + "#len"])]
+            return node
+
+        eng.P = fix(root, [])
+        for name in ("deconv", "heads", "blocks"):
+            eng.P.setdefault(name, [])
+        return eng
 
     # ------------------------------------------------------------------ weights
     def _dev(self, arr, dtype):
@@ -262,6 +340,8 @@ class LitePoseEngine(object):
     def run(self, x, flip=False, out_fp32=True, clone=True):
         """x: NCHW fp16/fp32 CUDA tensor.  Returns [out0 [N,2J,H/4,W/4], out1 [N,J,H/2,W/2]]
         (fp32 when out_fp32 else fp16).  ``flip`` computes the forward of torch.flip(x,[3])."""
+        if self.device.type != "cuda":
+            raise RuntimeError("LitePoseEngine.run needs a CUDA device (this engine was prepared on %s)" % self.device)
         assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
         if x.dtype not in (torch.float16, torch.float32):
             x = x.float()

@@ -137,3 +137,22 @@ def test_shipped_arch_golden_fp16_rowsum_depthwise(golden_dir, name, size):
         lib.lp_set_dw_precision(0)
     _tol(o[0].cpu().numpy(), z["out0"], name + " prec1 out0")
     _tol(o[1].cpu().numpy(), z["out1"], name + " prec1 out1")
+
+
+def test_folded_checkpoint_engine_matches(tmp_path):
+    """engine built from the offline folded checkpoint == engine built from the state_dict (bit for bit)"""
+    from litepose_b200.engine import LitePoseEngine
+    cfg = get_cfg(input_size=128)
+    arch = get_arch("XS")
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, arch), 1).eval()
+    x = synth.make_frames(2, 128, seed=11).cuda().half()
+    a = LitePoseEngine(model.state_dict(), arch, "cuda")
+    path = str(tmp_path / "m.folded.npz")
+    LitePoseEngine(model.state_dict(), arch, "cpu").export_folded(path)       # converted without a GPU
+    b = LitePoseEngine.from_folded(path, "cuda")
+    for flip in (False, True):
+        oa = a.run(x, flip=flip, out_fp32=True, clone=True)
+        ob = b.run(x, flip=flip, out_fp32=True, clone=True)
+        for u, v in zip(oa, ob):
+            assert torch.equal(u, v)

@@ -121,3 +121,39 @@ def test_gather_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res.shape == (5, 7) and np.array_equal(res[:, 0], np.arange(5) + 0.5)
+
+
+def test_folded_checkpoint_roundtrip(tmp_path):
+    """the folded, kernel-packed checkpoint reproduces every array the engine prepared (CPU is
+    enough for preparation; running needs CUDA and says so)."""
+    import torch
+    from litepose_b200.config import get_arch, get_cfg
+    from litepose_b200.engine import LitePoseEngine
+    from litepose_b200.lib.models.pose_mobilenet import get_pose_net
+    from litepose_b200 import synth
+    arch = get_arch("XS")
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(get_cfg(), False, arch), 1).eval()
+    eng = LitePoseEngine(model.state_dict(), arch, "cpu")
+    path = str(tmp_path / "xs.folded.npz")
+    eng.export_folded(path)
+    back = LitePoseEngine.from_folded(path, "cpu")
+
+    def same(a, b, where=""):
+        if isinstance(a, dict):
+            assert set(a) == set(b), where
+            for k in a:
+                same(a[k], b[k], where + "/" + str(k))
+        elif isinstance(a, list):
+            assert len(a) == len(b), where
+            for i, (x, y) in enumerate(zip(a, b)):
+                same(x, y, where + "/%d" % i)
+        elif torch.is_tensor(a):
+            assert a.dtype == b.dtype and torch.equal(a, b), where
+        else:
+            assert a == b, where
+
+    same(eng.P, back.P)
+    assert back.channels == eng.channels and back.arch == arch
+    with pytest.raises(RuntimeError):
+        back.run(torch.zeros(1, 3, 64, 64))
