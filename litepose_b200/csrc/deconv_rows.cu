@@ -398,7 +398,7 @@ bool deconv_rows_shape_ok(int W) {
         const char* e = getenv("LP_DECONV_ROWS");
         mode = (e && e[0] == '0') ? 0 : 1;
     }
-    return mode != 0 && W >= 96;
+    return mode != 0 && W >= 64;
 }
 
 int launch_deconv_rows(const void* refined, const void* raw, const void* w_rows, const float* bias_packed, void* out, int N,

@@ -4,26 +4,16 @@ whole batch with two kernel launches and one device->host copy."""
 import torch
 
 from . import plugins
+from ..lib.core.group import Params as _CoreParams
 
 
-class Params(object):
-    """nano_demo/fast_utils/group.py:10-31."""
+class Params(_CoreParams):
+    """The demo's Params (nano_demo/fast_utils/group.py:10-31) = the evaluation parser's fields
+    (litepose_b200.lib.core.group.Params) plus the peak window."""
 
     def __init__(self, cfg):
-        self.num_joints = cfg.DATASET.NUM_JOINTS
-        self.max_num_people = cfg.DATASET.MAX_NUM_PEOPLE
-        self.detection_threshold = cfg.TEST.DETECTION_THRESHOLD
-        self.tag_threshold = cfg.TEST.TAG_THRESHOLD
-        self.use_detection_val = cfg.TEST.USE_DETECTION_VAL
-        self.ignore_too_much = cfg.TEST.IGNORE_TOO_MUCH
+        super().__init__(cfg)
         self.window_size = cfg.TEST.NMS_KERNEL
-        if cfg.DATASET.WITH_CENTER and cfg.TEST.IGNORE_CENTER:
-            self.num_joints -= 1
-        if cfg.DATASET.WITH_CENTER and not cfg.TEST.IGNORE_CENTER:
-            order = [18, 1, 2, 3, 4, 5, 6, 7, 12, 13, 8, 9, 10, 11, 14, 15, 16, 17]
-        else:
-            order = [1, 2, 3, 4, 5, 6, 7, 12, 13, 8, 9, 10, 11, 14, 15, 16, 17]
-        self.joint_order = [i - 1 for i in order]
 
 
 class HeatmapParser(object):
