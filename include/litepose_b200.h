@@ -176,6 +176,14 @@ int lp_adjust_refine_f32(const float* det, const float* tag, int N, int J, int H
                          int do_adjust, int do_refine, void* workspace, size_t workspace_bytes,
                          lp_stream_t stream);
 
+/* ---- final predictions ("next" row 3, post-processing side) ----------------------
+ * get_final_preds (lib/utils/transforms.py:195-202): in place, x and y of every keypoint of
+ * the first min(num_people[n], pcap) persons of image n go through trans[n] (row-major 2x3
+ * float64, get_affine_transform(center, scale, 0, heatmap_size, inv=1)) in float64 and are
+ * stored back as float32.  ans [N,pcap,J,row] f32 (row >= 2: x, y, ...). */
+int lp_transform_preds_f32(float* ans, const int32_t* num_people, const double* trans, int N,
+                           int pcap, int J, int row, lp_stream_t stream);
+
 /* ---- fast_utils plugin on the GPU ("next" row 2) -------------------------------
  * The reference's own native grouping for its "fast inference" demo parser
  * (nano_demo/fast_utils/group.py:38-47), batched over N images.

@@ -289,3 +289,36 @@ extern "C" int lp_adjust_refine_f32(const float* det, const float* tag, int N, i
     }
     return LP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- final predictions
+// get_final_preds (reference lib/utils/transforms.py:195-202 -> transform_preds :50-57 -> affine_transform :101-104):
+// x, y of every keypoint of every found person go through the image's inverse affine (2x3, float64) and are stored
+// back as float32.  np.dot(t, [x, y, 1.]) on the reference's host evaluates each row as fma(t0, x, t1*y) + t2
+// (OpenBLAS dgemv, determined against numpy in the build container); the same order is used here.
+namespace lp {
+__global__ void transform_preds_kernel(float* __restrict__ ans, const int* __restrict__ num, const double* __restrict__ trans,
+                                       int pcap, int J, int row) {
+    const int n = blockIdx.y;
+    const int np_ = min(num[n], pcap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (person, joint)
+    if (i >= np_ * J) return;
+    const double* t = trans + (size_t)n * 6;
+    float* p = ans + ((size_t)n * pcap * J + i) * row;
+    const double x = (double)p[0], y = (double)p[1];
+    const double nx = __dadd_rn(__fma_rn(t[0], x, __dmul_rn(t[1], y)), t[2]);
+    const double ny = __dadd_rn(__fma_rn(t[3], x, __dmul_rn(t[4], y)), t[5]);
+    p[0] = __double2float_rn(nx);
+    p[1] = __double2float_rn(ny);
+}
+}  // namespace lp
+
+extern "C" int lp_transform_preds_f32(float* ans, const int32_t* num_people, const double* trans, int N, int pcap, int J,
+                                      int row, lp_stream_t stream) {
+    LP_CHECK_ARG(ans && num_people && trans, "lp_transform_preds_f32: null pointer");
+    LP_CHECK_ARG(N > 0 && N <= 65535 && pcap > 0 && J > 0 && row >= 2, "lp_transform_preds_f32: bad shape N=%d pcap=%d J=%d row=%d",
+                 N, pcap, J, row);
+    dim3 grid((pcap * J + 127) / 128, N);
+    lp::transform_preds_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(ans, num_people, trans, pcap, J, row);
+    LP_LAUNCH_CHECK("transform_preds_kernel");
+    return LP_OK;
+}

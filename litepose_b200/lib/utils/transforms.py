@@ -1,0 +1,144 @@
+"""Drop-in for the coordinate half of the reference's ``lib/utils/transforms.py`` used by valid.py:199-233
+(post-processing side): ``get_multi_scale_size`` (:155-180), ``get_affine_transform``
+(:60-98), ``affine_transform`` (:101-104), ``transform_preds`` (:50-57) and ``get_final_preds`` (:195-202).
+
+No OpenCV: ``cv2.getAffineTransform`` (a 6x6 solve in double) is restated as OpenCV does it - interleaved x/y
+equations, LU with partial pivoting, back substitution - and is bit-identical to cv2 4.13 on the reference's call
+patterns (tests/golden/transforms.npz, generated from the unmodified reference).
+
+``get_final_preds`` accepts what ``HeatmapParser.parse`` returns (host arrays) like the reference, or - for whole
+batches - the packed DEVICE result of the pipeline, in which case the inverse affine of every keypoint runs in one
+kernel (lp_transform_preds_f32) before the device->host copy.
+
+Not provided: ``resize_align_multi_scale``'s image warp (cv2.warpAffine) - the pre-processing side of row 3.
+"""
+import numpy as np
+
+
+def get_dir(src_point, rot_rad):
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    return [src_point[0] * cs - src_point[1] * sn, src_point[0] * sn + src_point[1] * cs]
+
+
+def get_3rd_point(a, b):
+    direct = a - b
+    return b + np.array([-direct[1], direct[0]], dtype=np.float32)
+
+
+def _affine_from_points(src, dst):
+    """cv2.getAffineTransform(src, dst) for float32 [3,2] point sets -> float64 [2,3]."""
+    a = np.zeros((6, 6), np.float64)
+    b = np.zeros(6, np.float64)
+    for i in range(3):
+        a[2 * i, 0] = a[2 * i + 1, 3] = src[i, 0]
+        a[2 * i, 1] = a[2 * i + 1, 4] = src[i, 1]
+        a[2 * i, 2] = a[2 * i + 1, 5] = 1.0
+        b[2 * i], b[2 * i + 1] = dst[i, 0], dst[i, 1]
+    m = 6
+    for i in range(m):
+        k = i
+        for j in range(i + 1, m):
+            if abs(a[j, i]) > abs(a[k, i]):
+                k = j
+        if k != i:
+            a[[i, k], i:] = a[[k, i], i:]
+            b[[i, k]] = b[[k, i]]
+        if a[i, i] == 0.0:
+            return np.zeros((2, 3), np.float64)           # singular: OpenCV returns zeros
+        d = -1.0 / a[i, i]
+        for j in range(i + 1, m):
+            alpha = a[j, i] * d
+            for c in range(i + 1, m):
+                a[j, c] += alpha * a[i, c]
+            b[j] += alpha * b[i]
+    for i in range(m - 1, -1, -1):
+        s = b[i]
+        for c in range(i + 1, m):
+            s -= a[i, c] * b[c]
+        b[i] = s / a[i, i]
+    return b.reshape(2, 3)
+
+
+def _triangle(center, direction, offset):
+    """The three float32 control points the reference builds: centre (+offset), centre + direction (+offset) - summed
+    in the reference's order - and the point that makes a right angle of the two (get_3rd_point)."""
+    pts = np.zeros((3, 2), dtype=np.float32)
+    pts[0, :] = center + offset
+    pts[1, :] = center + direction + offset
+    pts[2:, :] = get_3rd_point(pts[0, :], pts[1, :])
+    return pts
+
+
+def get_affine_transform(center, scale, rot, output_size, shift=np.array([0, 0], dtype=np.float32), inv=0):
+    """transforms.py:60-98 (same dtype promotions: float64 arithmetic, float32 control points)."""
+    if not isinstance(scale, (np.ndarray, list)):
+        scale = np.array([scale, scale])
+    box = scale * 200.0
+    out_w, out_h = output_size[0], output_size[1]
+    src = _triangle(center, get_dir([0, box[0] * -0.5], np.pi * rot / 180), box * shift)
+    # destination: centre of the output, direction straight up by half its width
+    dst = np.zeros((3, 2), dtype=np.float32)
+    dst[0, :] = [out_w * 0.5, out_h * 0.5]
+    dst[1, :] = np.array([out_w * 0.5, out_h * 0.5]) + np.array([0, out_w * -0.5], np.float32)
+    dst[2:, :] = get_3rd_point(dst[0, :], dst[1, :])
+    return _affine_from_points(dst, src) if inv else _affine_from_points(src, dst)
+
+
+def affine_transform(pt, t):
+    """transforms.py:101-104."""
+    return np.dot(t, np.array([pt[0], pt[1], 1.]).T)[:2]
+
+
+def transform_preds(coords, center, scale, output_size):
+    """transforms.py:50-57: rows of coords are (x, y, ...); x, y are mapped, the rest is kept."""
+    trans = get_affine_transform(center, scale, 0, output_size, inv=1)
+    out = coords.copy()
+    for row in range(coords.shape[0]):
+        out[row, 0:2] = affine_transform(coords[row, 0:2], trans)
+    return out
+
+
+def _up64(v):
+    return int((v + 63) // 64 * 64)
+
+
+def get_multi_scale_size(image, input_size, current_scale, min_scale):
+    """transforms.py:155-180: the shorter image side becomes input_size (rounded up to 64), the longer one keeps the
+    aspect ratio rounded up to 64; scale is the covered extent in units of 200 px."""
+    h, w, _ = image.shape
+    center = np.array([int(w / 2.0 + 0.5), int(h / 2.0 + 0.5)])
+    short = _up64(min_scale * input_size)
+    if w < h:
+        w_r = int(short * current_scale / min_scale)
+        h_r = int(_up64(short / w * h) * current_scale / min_scale)
+        scale = np.array([w / 200.0, h_r / w_r * w / 200.0])
+    else:
+        h_r = int(short * current_scale / min_scale)
+        w_r = int(_up64(short / h * w) * current_scale / min_scale)
+        scale = np.array([w_r / h_r * h / 200.0, h / 200.0])
+    return (w_r, h_r), center, scale
+
+
+def get_final_preds(grouped_joints, center, scale, heatmap_size):
+    """transforms.py:195-202; grouped_joints = what HeatmapParser.parse returned ([persons]); image 0."""
+    return [transform_preds(person, center, scale, heatmap_size) for person in grouped_joints[0]]
+
+
+def final_preds_device(ans, num, centers, scales, heatmap_size):
+    """Whole batch on the device, in place: ans [N,P,J,3+T] float32 CUDA (DeviceParser / pipeline layout), num [N]
+    int32 CUDA; centers [N,2], scales [N,2] host arrays.  Every keypoint of every found person gets the inverse
+    affine of its image (the same float64 arithmetic as affine_transform, rounded to float32 on store)."""
+    import torch
+
+    from litepose_b200 import _lib
+    n = ans.shape[0]
+    trans = np.stack([get_affine_transform(np.asarray(centers[i]), np.asarray(scales[i]), 0, heatmap_size, inv=1)
+                      for i in range(n)]).reshape(n, 6)
+    t = torch.from_numpy(np.ascontiguousarray(trans)).to(ans.device)
+    lib = _lib.load()
+    with torch.cuda.device(ans.device):
+        _lib.check(lib.lp_transform_preds_f32(ans.data_ptr(), num.data_ptr(), t.data_ptr(), n, ans.shape[1],
+                                              ans.shape[2], ans.shape[3],
+                                              torch.cuda.current_stream(ans.device).cuda_stream),
+                   "lp_transform_preds_f32")
+    return ans

@@ -91,6 +91,25 @@ class LitePosePipeline(object):
         self.two_streams = os.environ.get("LP_TWO_STREAMS", "1") != "0"
         self.keep = keep                  # persons copied back per image in the fixed-size D2H payload
         self._state = {}
+        self._final = None                # per-image inverse affines of get_final_preds (host, [N,6] float64)
+
+    def set_final_preds(self, centers=None, scales=None):
+        """valid.py:230-233 on the device: after this call every step maps the keypoints of image i back to its original
+        image with get_affine_transform(centers[i], scales[i], 0, [Wd, Hd], inv=1) (reference lib/utils/transforms.py
+        :50-57,195-202) before they are packed for the host.  The 2x3 matrices are computed here, once, on the host
+        (they depend on the image sizes only); call again when the batch composition changes, or with None to get
+        heat-map coordinates back."""
+        if centers is None:
+            self._final = None
+            return
+        import numpy as np
+        from .lib.utils.transforms import get_affine_transform
+        self._final = (np.asarray(centers, np.float64), np.asarray(scales, np.float64))
+        self._final_ver = getattr(self, "_final_ver", 0) + 1
+        self._final_trans = {}
+        self._get_trans = lambda hm: self._final_trans.setdefault(tuple(hm), np.stack([
+            get_affine_transform(np.asarray(c), np.asarray(s), 0, list(hm), inv=1)
+            for c, s in zip(*self._final)]).reshape(-1, 6))
 
     # -- device step (everything between the H2D copy and the D2H copy) -------------
     def _device_step(self, st, x):
@@ -119,6 +138,10 @@ class LitePosePipeline(object):
         if st["plant"] is not None:
             st["plant"].apply(st["det"], st["tag"])
         ans, num, scores = self.parser.run(st["det"], st["tag"], self.adjust, self.refine)
+        if st["trans"] is not None:
+            _lib.check(self.lib.lp_transform_preds_f32(ans.data_ptr(), num.data_ptr(), st["trans"].data_ptr(), n,
+                                                       ans.shape[1], ans.shape[2], ans.shape[3],
+                                                       torch.cuda.current_stream().cuda_stream), "lp_transform_preds_f32")
         k = self.keep
         st["packed"][:, :k * st["row"]].copy_(ans[:, :k].reshape(n, -1))
         st["packed"][:, k * st["row"]:k * st["row"] + k].copy_(scores[:, :k])
@@ -126,7 +149,7 @@ class LitePosePipeline(object):
         return st["packed"]
 
     def _get_state(self, n, s_h, s_w, dtype, plant):
-        key = (n, s_h, s_w, dtype)
+        key = (n, s_h, s_w, dtype, self._final is not None)
         st = self._state.get(key)
         if st is None:
             J = self.params.num_joints
@@ -141,10 +164,18 @@ class LitePosePipeline(object):
                 "tag": torch.empty((n, J, Hd, Wd, T), dtype=torch.float32, device=dev),
                 "packed": torch.zeros((n, self.keep * row + self.keep + 1), dtype=torch.float32, device=dev),
                 "host": torch.empty((n, self.keep * row + self.keep + 1), dtype=torch.float32).pin_memory(),
-                "row": row, "T": T, "graph": None, "plant": plant,
+                "row": row, "T": T, "graph": None, "plant": plant, "trans": None,
             }
+            if self._final is not None:
+                st["trans"] = torch.zeros((n, 6), dtype=torch.float64, device=dev)
             self._state[key] = st
         st["plant"] = plant
+        if st["trans"] is not None and st.get("trans_ver") != self._final_ver:
+            if len(self._final[0]) != n:
+                raise ValueError("set_final_preds: %d centers for a batch of %d" % (len(self._final[0]), n))
+            tr = self._get_trans((st["det"].shape[3], st["det"].shape[2]))
+            st["trans"].copy_(torch.from_numpy(tr))          # read by the (captured) kernel at replay time
+            st["trans_ver"] = self._final_ver
         return st
 
     def step_device(self, x_dev, plant=None):

@@ -156,3 +156,32 @@ def test_folded_checkpoint_engine_matches(tmp_path):
         ob = b.run(x, flip=flip, out_fp32=True, clone=True)
         for u, v in zip(oa, ob):
             assert torch.equal(u, v)
+
+
+def test_pipeline_final_preds_on_device():
+    """valid.py:230-233 inside the step: keypoints mapped back to the original image by the device kernel equal the
+    oracle parser's keypoints pushed through the host get_final_preds (reference arithmetic)."""
+    from litepose_b200.lib.utils import transforms as T
+    from litepose_b200.pipeline import LitePosePipeline, PlantedCrowd
+    cfg = get_cfg(input_size=128)
+    arch = get_arch("XS")
+    torch.manual_seed(0)
+    model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, arch), 1)).eval().cuda()
+    n = 3
+    frames = synth.make_frames(n, 128, seed=5).half().pin_memory()
+    plant = PlantedCrowd(n, 14, 128, 128, 2, num_people=3, seed=4, device="cuda")
+    pipe = LitePosePipeline(model, cfg, use_graphs=True)
+    plain = pipe.step(frames, plant)                          # heat-map coordinates
+    sizes = [(480, 640), (640, 427), (333, 500)]              # original (h, w) of the three images
+    cs = [T.get_multi_scale_size(np.zeros((h, w, 3), np.uint8), 128, 1.0, 1.0)[1:] for h, w in sizes]
+    pipe.set_final_preds([c for c, _ in cs], [s for _, s in cs])
+    for _ in range(2):                                        # second call replays the captured graph
+        mapped = pipe.step(frames, plant)
+    for i in range(n):
+        a, b = plain[i], mapped[i]
+        assert a[2] == b[2] and a[2] > 0
+        exp = T.get_final_preds([list(a[0])], cs[i][0], cs[i][1], [128, 128])
+        assert np.array_equal(np.stack(exp), b[0])
+    pipe.set_final_preds(None)
+    again = pipe.step(frames, plant)
+    assert all(np.array_equal(x[0], y[0]) for x, y in zip(plain, again))
