@@ -176,6 +176,19 @@ int lp_adjust_refine_f32(const float* det, const float* tag, int N, int J, int H
                          int do_adjust, int do_refine, void* workspace, size_t workspace_bytes,
                          lp_stream_t stream);
 
+/* ---- pre-processing ("next" row 3, pre side) -------------------------------------
+ * resize_align_multi_scale's image warp (lib/utils/transforms.py:183-192:
+ * cv2.warpAffine(image, trans, size), INTER_LINEAR, BORDER_CONSTANT 0) restated exactly in
+ * OpenCV's fixed-point arithmetic, optionally followed by torchvision ToTensor + Normalize
+ * (valid.py:172-186,212) in IEEE float32.  img: N x [H][W][3] uint8 (device); minv [N,6]
+ * float64 (device) = the INVERTED 2x3 matrices (dst -> src), inverted on
+ * the host in OpenCV's operation order (litepose_b200.lib.utils.transforms.invert_affine);
+ * mean/std: 3 floats each (HOST pointers, read at call time).
+ * out_mode 0: uint8 [N][out_h][out_w][3]; 1: float32 [N,3,out_h,out_w]; 2: float16 NCHW. */
+int lp_warp_affine_normalize_u8(const uint8_t* img, int N, int H, int W, const double* minv,
+                                int out_w, int out_h, const float* mean, const float* std, void* out,
+                                int out_mode, lp_stream_t stream);
+
 /* ---- final predictions ("next" row 3, post-processing side) ----------------------
  * get_final_preds (lib/utils/transforms.py:195-202): in place, x and y of every keypoint of
  * the first min(num_people[n], pcap) persons of image n go through trans[n] (row-major 2x3

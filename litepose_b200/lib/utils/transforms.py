@@ -10,7 +10,9 @@ patterns (tests/golden/transforms.npz, generated from the unmodified reference).
 batches - the packed DEVICE result of the pipeline, in which case the inverse affine of every keypoint runs in one
 kernel (lp_transform_preds_f32) before the device->host copy.
 
-Not provided: ``resize_align_multi_scale``'s image warp (cv2.warpAffine) - the pre-processing side of row 3.
+``resize_align_multi_scale`` (:183-192) warps on the GPU: cv2.warpAffine's 8-bit fixed-point arithmetic is restated
+exactly in lp_warp_affine_normalize_u8 (bit-identical images); ``resize_align_normalize_device`` additionally applies
+torchvision's ToTensor + Normalize (valid.py:172-186,212) in the same kernel and leaves the NCHW tensor on the device.
 """
 import numpy as np
 
@@ -122,6 +124,65 @@ def get_multi_scale_size(image, input_size, current_scale, min_scale):
 def get_final_preds(grouped_joints, center, scale, heatmap_size):
     """transforms.py:195-202; grouped_joints = what HeatmapParser.parse returned ([persons]); image 0."""
     return [transform_preds(person, center, scale, heatmap_size) for person in grouped_joints[0]]
+
+
+def invert_affine(m):
+    """The dst->src matrix cv2.warpAffine derives from the src->dst one (OpenCV imgwarp.cpp, same operation order)."""
+    m = [float(v) for v in np.asarray(m, np.float64).ravel()]
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0], m[1], m[3], m[4] = a11, m[1] * -d, m[3] * -d, a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return np.array(m, np.float64)
+
+
+def _warp(images, sizes_hw, input_size, current_scale, min_scale, mode, mean=None, std=None):
+    import torch
+
+    from litepose_b200 import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("litepose_b200 pre-processing runs on a CUDA device (no CPU fallback)")
+    if torch.is_tensor(images):
+        img = images
+    else:
+        img = torch.from_numpy(np.ascontiguousarray(images))
+    if img.dim() == 3:
+        img = img.unsqueeze(0)
+    if img.dtype != torch.uint8 or img.shape[3] != 3:
+        raise TypeError("images must be uint8 [N,H,W,3] (or [H,W,3])")
+    n, h, w, _ = img.shape
+    size, center, scale = get_multi_scale_size(np.empty((h, w, 3), np.uint8), input_size, current_scale, min_scale)
+    minv = invert_affine(get_affine_transform(center, scale, 0, size))
+    dev = img.device if img.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    d_img = img.to(dev, non_blocking=True).contiguous()
+    d_m = torch.from_numpy(np.tile(minv, (n, 1))).to(dev)
+    shape = (n, size[1], size[0], 3) if mode == 0 else (n, 3, size[1], size[0])
+    out = torch.empty(shape, dtype=(torch.uint8, torch.float32, torch.float16)[mode], device=dev)
+    mean_a = np.asarray(mean if mean is not None else (0, 0, 0), np.float32)
+    std_a = np.asarray(std if std is not None else (1, 1, 1), np.float32)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.lp_warp_affine_normalize_u8(d_img.data_ptr(), n, h, w, d_m.data_ptr(), size[0], size[1],
+                                                   mean_a.ctypes.data, std_a.ctypes.data, out.data_ptr(), mode,
+                                                   torch.cuda.current_stream(dev).cuda_stream),
+                   "lp_warp_affine_normalize_u8")
+    return out, center, scale
+
+
+def resize_align_multi_scale(image, input_size, current_scale, min_scale):
+    """transforms.py:183-192, same return types: (uint8 image [h_resized, w_resized, 3] on the host, center, scale).
+    The warp itself runs on the GPU."""
+    out, center, scale = _warp(image, None, input_size, current_scale, min_scale, 0)
+    return out[0].cpu().numpy(), center, scale
+
+
+def resize_align_normalize_device(images, input_size, current_scale, min_scale, mean, std, half=False):
+    """valid.py:210-213 for a batch of equally sized images without leaving the device: warp, ToTensor, Normalize ->
+    NCHW float32 (or float16 = what tofp16 would make of it) CUDA tensor, plus center and scale (shared: same size)."""
+    return _warp(images, None, input_size, current_scale, min_scale, 2 if half else 1, mean, std)
 
 
 def final_preds_device(ans, num, centers, scales, heatmap_size):

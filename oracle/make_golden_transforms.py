@@ -27,6 +27,19 @@ def keypoints(seed, persons, joints, t, hm_w, hm_h):
     return out
 
 
+PRE_CASES = [  # (seed, h, w, input_size): small images, full outputs stored
+    (1, 97, 123, 128), (2, 150, 101, 128), (3, 64, 64, 64), (4, 45, 200, 64), (5, 240, 320, 256),
+]
+MEAN, STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]          # valid.py:181-184
+
+
+def pre_image(seed, h, w):
+    rs = np.random.RandomState(seed)
+    img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    img[h // 4:h // 2, w // 4:w // 2] = rs.randint(0, 256, 3).astype(np.uint8)      # a flat patch
+    return img
+
+
 def load_reference():
     spec = importlib.util.spec_from_file_location("ref_transforms", "/root/reference/lib/utils/transforms.py")
     mod = importlib.util.module_from_spec(spec)
@@ -49,6 +62,15 @@ def main():
         out[pre + "center"], out[pre + "scale"] = np.asarray(center), np.asarray(scale)
         out[pre + "fwd"], out[pre + "inv"] = fwd, inv
         out[pre + "final"] = np.stack(final)
+    import torchvision.transforms as tvt
+    tf = tvt.Compose([tvt.ToTensor(), tvt.Normalize(mean=MEAN, std=STD)])       # valid.py:178-186
+    for i, (seed, h, w, size) in enumerate(PRE_CASES):
+        img = pre_image(seed, h, w)
+        resized, center, scale = ref.resize_align_multi_scale(img, size, 1.0, 1.0)
+        pre = "p%02d_" % i
+        out[pre + "resized"] = resized
+        out[pre + "tensor"] = tf(resized).numpy()
+        out[pre + "center"], out[pre + "scale"] = np.asarray(center), np.asarray(scale)
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "transforms.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

@@ -49,3 +49,35 @@ def test_final_preds_device_matches_reference_golden():
         for k, i in enumerate(idx):
             assert np.array_equal(out[k, :num[k]], g["c%02d_final" % i]), i
             assert (out[k, num[k]:] == -3.0).all()               # rows of absent persons are untouched
+
+
+@pytest.mark.gpu
+def test_preprocessing_device_matches_reference_golden():
+    """resize_align_multi_scale (cv2.warpAffine restated in fixed point) and ToTensor + Normalize on the device against
+    images / tensors produced by the unmodified reference + torchvision: bit for bit."""
+    from oracle.make_golden_transforms import MEAN, PRE_CASES, STD, pre_image
+    g = np.load(GOLD)
+    for i, (seed, h, w, size) in enumerate(PRE_CASES):
+        img = pre_image(seed, h, w)
+        pre = "p%02d_" % i
+        resized, center, scale = T.resize_align_multi_scale(img, size, 1.0, 1.0)
+        assert resized.dtype == np.uint8 and np.array_equal(resized, g[pre + "resized"]), i
+        assert np.array_equal(center, g[pre + "center"]) and np.array_equal(scale, g[pre + "scale"]), i
+        # a batch of two identical images, normalised on the device
+        batch = torch.from_numpy(np.stack([img, img])).cuda()
+        t32, _, _ = T.resize_align_normalize_device(batch, size, 1.0, 1.0, MEAN, STD)
+        assert t32.dtype == torch.float32 and np.array_equal(t32[1].cpu().numpy(), g[pre + "tensor"]), i
+        t16, _, _ = T.resize_align_normalize_device(batch, size, 1.0, 1.0, MEAN, STD, half=True)
+        assert torch.equal(t16.cpu(), torch.from_numpy(g[pre + "tensor"]).half()[None].expand(2, -1, -1, -1))
+
+
+@pytest.mark.gpu
+def test_preprocessing_device_matches_cv2_at_full_size():
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(7)
+    for h, w, size in ((480, 640, 512), (640, 427, 512), (1080, 1920, 640)):
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        dims, center, scale = T.get_multi_scale_size(img, size, 1.0, 1.0)
+        expect = cv2.warpAffine(img, T.get_affine_transform(center, scale, 0, dims), dims)
+        got, _, _ = T.resize_align_multi_scale(img, size, 1.0, 1.0)
+        assert np.array_equal(got, expect), (h, w, size)
