@@ -379,6 +379,35 @@ def time_variants(args, model, x_dev, plant, device, iters=5):
     except Exception as e:
         fast["cpu_port_error"] = str(e)[:120]
     out["fast_utils_parser"] = fast
+    # (c) the whole valid.py loop body on the device (8(f) row 3): uint8 camera-order images in pinned host memory ->
+    # H2D -> warpAffine + ToTensor + Normalize -> the bench step -> get_final_preds -> packed keypoints on the host
+    try:
+        from litepose_b200.lib.utils import transforms as T
+        pipe_full = LitePosePipeline(model, get_cfg(input_size=S), use_graphs=True)
+        rs = np.random.RandomState(5)
+        imgs = torch.from_numpy(rs.randint(0, 256, (B, S, S, 3)).astype(np.uint8)).pin_memory()
+        _, center, scale = T.get_multi_scale_size(np.empty((S, S, 3), np.uint8), S, 1.0, 1.0)
+        pipe_full.set_final_preds([center] * B, [scale] * B)
+        mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+        host = None
+
+        def full():
+            nonlocal host
+            d = imgs.to(device, non_blocking=True)
+            x, _, _ = T.resize_align_normalize_device(d, S, 1.0, 1.0, mean, std, half=True)
+            packed = pipe_full.step_device(x, plant)
+            if host is None:
+                host = torch.empty(packed.shape, dtype=packed.dtype).pin_memory()
+            host.copy_(packed, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        tf = timed(full, iters)
+        out["from_uint8_images"] = {"frames_per_s": B / tf, "ms_per_step": tf * 1e3,
+                                    "what": "uint8 HWC frames (pinned host) -> device warpAffine+ToTensor+Normalize -> bench "
+                                            "step -> get_final_preds on the device -> keypoints on the host, synchronous"}
+        del pipe_full
+    except Exception as e:
+        out["from_uint8_images"] = {"error": str(e)[:200]}
     del pipe_fast
     torch.cuda.empty_cache()
     return out
