@@ -71,7 +71,7 @@ struct __align__(8) GemmBarriers {
     uint64_t empty[MAX_STAGES];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
-    uint64_t res_full;
+    uint64_t res_full[2];
     uint64_t bres_full;
     uint32_t tmem_base;
     uint32_t pad;
@@ -103,7 +103,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tma_prefetch_desc(&mapOut);
             if (p.residual) tma_prefetch_desc(&mapRes);
         }
-        mbar_init(&bars->res_full, 1);
+        mbar_init(&bars->res_full[0], 1);
+        mbar_init(&bars->res_full[1], 1);
         mbar_init(&bars->bres_full, 1);
         for (int i = 0; i < MAX_STAGES; ++i) {
             mbar_init(&bars->full[i], 1);
@@ -111,7 +112,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->tmem_full[i], 1);
-            mbar_init(&bars->tmem_empty[i], EPI_THREADS / 32);
+            // MODE_PW with <= 128 output columns: each accumulator buffer is drained by ONE group of four epilogue warps
+            mbar_init(&bars->tmem_empty[i], (MODE == MODE_PW && p.n_tile <= 128) ? EPI_THREADS / 64 : EPI_THREADS / 32);
         }
         fence_barrier_init();
     }
@@ -232,8 +234,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;          // the two warps of a quarter take alternate 16-column groups
         const int row = q * 32 + lane;
-        int it = 0;
-        for (int t = t_begin; t < t_end; t += t_step, ++it) {
+        // MODE_PW, tiles of <= 128 columns: the two groups of four warps work on ALTERNATE tiles (group g drains TMEM
+        // buffer g through staging buffer g with its own named barrier and its own TMA store stream), so two tiles'
+        // epilogues are in flight and the latency chain tcgen05.ld -> convert -> st.shared -> TMA store of one tile
+        // hides behind the other's.  Wider tiles keep both groups on the same tile (alternate 16-column groups).
+        const bool split = (MODE == MODE_PW) && p.n_tile <= 128;
+        const int it0 = split ? half : 0, it_inc = split ? 2 : 1;
+        int it = it0;
+        for (int t = t_begin + it0 * t_step; t < t_end; t += it_inc * t_step, it += it_inc) {
             const int buf = it & 1;
             const int chunk = resident ? my_chunk : t % p.n_chunks;
             const int mt = resident ? t : t / p.n_chunks;
@@ -247,29 +255,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 // Output tile goes through a 128B-swizzled shared-memory staging buffer (conflict-free 16-byte
                 // st.shared) and leaves with TMA tensor stores (full 128-byte lines, rows/columns beyond M/N
                 // clipped by the tensor map); the residual tile arrives the same way.
-                const bool issuer = (threadIdx.x == 64);
+                const bool issuer = split ? (threadIdx.x == 64 + 128 * half) : (threadIdx.x == 64);
                 const int ncols = min(p.n_tile, p.N - chunk * p.n_tile);       // valid columns of this chunk
                 const int nsub = (ncols + 63) >> 6;
-                // staging: 4 sub-tile slots; tiles of <= 128 columns alternate between two slot groups so the TMA store
-                // of tile i drains while tile i+1 is being converted (one store group may stay in flight)
-                const int nsub_max = (p.n_tile + 63) >> 6;
-                const bool dbuf = nsub_max <= 2;
-                uint8_t* sStage = sOut + ((dbuf && (it & 1)) ? 2 * OUT_SUB : 0);
-                if (issuer) {
-                    if (dbuf) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // staging: 4 sub-tile slots.  split: group g owns slots 2g, 2g+1.  Otherwise the whole tile uses slots 0..
+                uint8_t* sStage = sOut + (split ? half * 2 * OUT_SUB : 0);
+                uint64_t* res_bar = &bars->res_full[split ? half : 0];
+                const uint32_t res_par = split ? ((it >> 1) & 1) : (it & 1);
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this issuer's previous store
+                if (split) {
+                    if (half) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else asm volatile("bar.sync 1, 128;" ::: "memory");
+                } else {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (p.residual && issuer) {   // residual tile is fetched while this tile's MMAs are still running
-                    mbar_expect_tx(&bars->res_full, nsub * OUT_SUB);
+                    mbar_expect_tx(res_bar, nsub * OUT_SUB);
                     for (int g = 0; g < nsub; ++g)
-                        tma_load_2d(sStage + g * OUT_SUB, &mapRes, &bars->res_full, chunk * p.n_tile + g * 64, mt * BM);
+                        tma_load_2d(sStage + g * OUT_SUB, &mapRes, res_bar, chunk * p.n_tile + g * 64, mt * BM);
                 }
                 mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
                 tc_fence_after();
-                if (p.residual) mbar_wait(&bars->res_full, it & 1);
+                if (p.residual) mbar_wait(res_bar, res_par);
                 uint8_t* srow = sStage + row * 128;
-                for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
+                for (int c0 = split ? 0 : half * 16; c0 < p.n_tile; c0 += split ? 16 : 32) {
                     tc_ld16(taddr + c0, r);
                     tc_wait_ld();
                     if (c0 < ncols) {
@@ -321,7 +330,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
                 fence_proxy_async();
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (split) {
+                    if (half) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else asm volatile("bar.sync 1, 128;" ::: "memory");
+                } else {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
                 if (issuer) {
                     for (int g = 0; g < nsub; ++g) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -394,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
         }
-        if (MODE == MODE_PW && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (MODE == MODE_PW && (threadIdx.x == 64 || threadIdx.x == 192)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
