@@ -422,18 +422,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 // ------------------------------------------------------------------ host side
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-// N <= 256: one chunk of round_up(N,16) MMA columns.  Wider layers are cut into chunks of 192 or 256 columns (a
-// multiple of the 64-column TMA store sub-tile, so stores of neighbouring chunks never overlap), whichever pads less.
+// N <= 160 (every projection, incl. the fused depthwise+projection kernel's single-chunk layout): one chunk of
+// round_up(N,16) MMA columns.  Wider layers (the 6x expansions) are cut into 128-column chunks: a multiple of the
+// 64-column TMA store sub-tile (stores of neighbouring chunks never overlap), and tiles of <= 128 columns let the two
+// epilogue warp groups drain alternate tiles.  (192/256-column chunks measured 0.9 % slower on the whole step.)
 static void pw_tiling(int N, int* n_chunks, int* n_tile) {
     const int np = round_up(N, 16);
-    if (np <= 256) {
+    if (np <= 160) {
         *n_chunks = 1;
         *n_tile = np;
         return;
     }
-    const int c192 = (np + 191) / 192, c256 = (np + 255) / 256;
-    if (c192 * 192 < c256 * 256) { *n_chunks = c192; *n_tile = 192; }
-    else { *n_chunks = c256; *n_tile = 256; }
+    *n_chunks = (np + 127) / 128;
+    *n_tile = 128;
 }
 
 static int set_smem_attr_once(const void* fn) {

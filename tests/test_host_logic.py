@@ -34,9 +34,11 @@ def test_c_abi_exports_match_header():
 def test_host_side_packers_and_errors():
     lib = _lib.load()
     assert lib.lp_pw1x1_packed_elems(16, 96) == 96 * 64
-    assert lib.lp_pw1x1_packed_elems(120, 720) == 3 * 2 * 256 * 64     # 720 -> 3 chunks of 256 MMA columns
+    assert lib.lp_pw1x1_packed_elems(120, 720) == 6 * 2 * 128 * 64     # 720 -> 6 chunks of 128 MMA columns
     assert lib.lp_pw1x1_packed_bias_elems(720) == 768
-    assert lib.lp_pw1x1_packed_elems(48, 288) == 2 * 1 * 192 * 64      # 288 -> 2 chunks of 192
+    assert lib.lp_pw1x1_packed_elems(48, 288) == 3 * 1 * 128 * 64      # 288 -> 3 chunks of 128
+    assert lib.lp_pw1x1_packed_elems(120, 160) == 2 * 160 * 64          # <= 160: one chunk (fused kernel layout)
+    assert lib.lp_pw1x1_packed_elems(32, 192) == 2 * 1 * 128 * 64       # 192 -> 128 + 64 (second chunk half empty)
     k, n = 24, 40
     w = (np.arange(n * k, dtype=np.float32).reshape(n, k) / 100).astype(np.float16).view(np.uint16)
     wp = np.zeros(lib.lp_pw1x1_packed_elems(k, n), np.uint16)
