@@ -7,12 +7,15 @@
 //               folded-BN bias + ReLU, written interleaved into the 2x up-sampled NHWC output
 //   MODE_HEAD   head pair:  out_nchw_f32 = A1 W1^T + A2 W2^T
 //
-// Structure per CTA (192 threads, 1 CTA/SM, grid = min(#tiles, #SMs)):
-//   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages)
+// Structure per CTA (320 threads, 1 CTA/SM, grid = min(#tiles, #SMs)):
+//   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring; MODE_PW may keep the weights of
+//                                  its N chunk resident and stream only activation tiles)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::f16, M=128, fp32 accumulators in TMEM,
 //                                  tcgen05.commit releases smem stages / publishes accumulators)
-//   warps 2..5    : epilogue      (tcgen05.ld 32x32b -> bias/act/residual -> global), overlapped with the next
-//                                  tile's MMAs through a double-buffered TMEM accumulator (2 x 256 columns)
+//   warps 2..9    : epilogue      (tcgen05.ld 32x32b -> bias/act/residual -> swizzled smem staging -> TMA store, or
+//                                  direct stores in the spatial modes), overlapped with the next tile's MMAs through a
+//                                  double-buffered TMEM accumulator (2 x 256 columns); two groups of four warps, one
+//                                  warp per TMEM lane quarter in each
 // A "step" is one 128-row x 64-channel activation tile (one TMA box; spatially shifted boxes with hardware
 // zero fill implement the deconv taps and all image borders) multiplied against 1..4 weight sub-tiles.
 #include "common.cuh"
