@@ -162,6 +162,29 @@ def cpu_reference_step(cfg, arch, sd, frames, plant):
     return out
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries print there too (NCCL announces its version on the
+    first communicator, cuDNN / torch warnings ...), so fd 1 is pointed at stderr for the life of the process and the
+    result line is written to a private duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -191,7 +214,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ roofline (dominant kernels)
@@ -416,6 +439,7 @@ def time_variants(args, model, x_dev, plant, device, iters=5):
 # ------------------------------------------------------------------------------ main arm
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -637,7 +661,7 @@ def main():
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "forward_only": fwd, "variants": variants,
         "persons_found_rank0": found[:8],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
