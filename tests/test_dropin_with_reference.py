@@ -1,6 +1,6 @@
 """CPU, build container only (skipped where /root/reference is absent): the sys.path shadowing
-of INTEGRATION.md §1 resolves `models.pose_mobilenet` / `core.group` to this repo and
-`core.inference` to the unmodified reference, and the reference glue runs on our module's outputs."""
+of INTEGRATION.md §1 resolves `models.pose_mobilenet` / `core.group` / `utils.transforms` to this repo and
+`core.inference`, `utils.zipreader` ... to the unmodified reference, and the reference glue runs on our module's outputs."""
 import os
 import subprocess
 import sys
@@ -30,6 +30,14 @@ with torch.no_grad():
     fh, tl = aggregate_results(cfg, 1, None, [], h, t)
 assert tuple(fh.shape) == (1, 14, 64, 64) and tuple(torch.cat(tl, 4).shape) == (1, 14, 64, 64, 2)
 HeatmapParser(cfg)
+# valid.py:44-46 and :27-29: the coordinate helpers come from this repo, the other utils modules from the reference
+from utils.transforms import resize_align_multi_scale, get_final_preds, get_multi_scale_size
+import utils.transforms, utils.zipreader
+assert "litepose_b200" in utils.transforms.__file__ and "%(ref)s" in utils.zipreader.__file__
+assert utils.transforms.fliplr_joints.__module__ == "_reference_utils_transforms"      # delegated, not restated
+import numpy as np
+size, center, scale = get_multi_scale_size(np.zeros((480, 640, 3), np.uint8), 512, 1.0, 1.0)
+assert size == (704, 512) and list(center) == [320, 240]
 print("dropin ok")
 '''
 
