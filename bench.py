@@ -567,8 +567,7 @@ def main():
         return
 
     # sanity: the planted persons are found
-    res = pipe.unpack(host_out[0], 14 * 5, 2)
-    found = [r[2] for r in res]
+    found = [int(v) for v in host_out[0][:, -1].tolist()]
 
     # ---- roofline of the dominant kernel (dw7x7 stage-0 shape of this workload)
     peaks = {}

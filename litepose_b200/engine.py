@@ -151,6 +151,12 @@ class LitePoseEngine(object):
     def _prep(self, sd):
         arch = self.arch
         P = {}
+        n_dec = len([k for k in sd if k.startswith("deconv_refined.") and k.endswith(".weight")])
+        if n_dec != 3 or tuple(sd["first.0.0.weight"].shape) != (32, 3, 3, 3):
+            raise ValueError("LitePoseEngine implements the shipped LitePose topology (32-channel 3x3 stem, "
+                             "MODEL.EXTRA.NUM_DECONV_LAYERS == 3, 4x4 stride-2 deconvs; reference "
+                             "lib/models/pose_mobilenet.py:36-135); this state_dict has %d deconv levels and a %s stem"
+                             % (n_dec, tuple(sd["first.0.0.weight"].shape)))
         s, b = _fold(sd, "first.0.1")
         w = sd["first.0.0.weight"].float() * s.view(-1, 1, 1, 1)
         P["stem"] = {"w": w.reshape(32, 27).half().contiguous().to(self.device),

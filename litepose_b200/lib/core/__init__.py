@@ -5,7 +5,12 @@ import os
 import sys
 
 _here = os.path.dirname(os.path.abspath(__file__))
-for _p in list(sys.path):
-    _cand = os.path.join(_p, "core")
-    if _p and os.path.isdir(_cand) and os.path.abspath(_cand) != _here and _cand not in __path__:
-        __path__.append(_cand)
+try:
+    from .._dynpath import DynPath
+except ImportError:
+    sys.path.insert(0, os.path.dirname(_here))
+    try:
+        from _dynpath import DynPath
+    finally:
+        sys.path.pop(0)
+__path__ = DynPath(_here, "core")

@@ -11,10 +11,15 @@ import sys
 from . import pose_mobilenet  # noqa: F401
 
 _here = os.path.dirname(os.path.abspath(__file__))
-for _p in list(sys.path):
-    _cand = os.path.join(_p, "models")
-    if _p and os.path.isdir(_cand) and os.path.abspath(_cand) != _here and _cand not in __path__:
-        __path__.append(_cand)
+try:
+    from .._dynpath import DynPath           # imported as litepose_b200.lib.models
+except ImportError:                          # imported as top-level ``models`` (lib/ on sys.path)
+    sys.path.insert(0, os.path.dirname(_here))
+    try:
+        from _dynpath import DynPath
+    finally:
+        sys.path.pop(0)
+__path__ = DynPath(_here, "models")
 
 
 def __getattr__(name):

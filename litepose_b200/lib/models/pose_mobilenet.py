@@ -66,10 +66,18 @@ class SepConv2d(nn.Module):
 
 
 class _EngineCache(object):
-    """Per-device compiled state; deliberately not copied by deepcopy / pickling."""
+    """Per-device compiled state; deliberately not copied by deepcopy / pickling.  One object is shared by a module
+    and its nn.DataParallel replicas (replicate() copies the module __dict__ shallowly), one engine per device, so
+    lookups / builds take the lock (DataParallel runs the replicas on threads, reference valid.py:165)."""
 
     def __init__(self):
+        import threading
         self.engines = {}
+        self.lock = threading.RLock()
+
+    def clear(self):
+        with self.lock:
+            self.engines.clear()
 
     def __deepcopy__(self, memo):
         return _EngineCache()
@@ -78,7 +86,7 @@ class _EngineCache(object):
         return {}
 
     def __setstate__(self, state):
-        self.engines = {}
+        self.__init__()
 
 
 class LitePose(nn.Module):
@@ -132,20 +140,38 @@ class LitePose(nn.Module):
 
     # -- engine management -------------------------------------------------
     def lp_invalidate(self):
-        """Drop the packed-weight cache (call after mutating parameters in place)."""
-        self._lp_cache.engines.clear()
+        """Drop the packed-weight cache.  Not needed after the usual mutations: .to()/.half(), load_state_dict,
+        train()/eval() switches and any in-place update of a parameter or buffer (optimizer step, BN statistics,
+        ``p.data.copy_``) are detected; call it after replacing ``p.data`` with a new tensor of version 0."""
+        self._lp_cache.clear()
 
     def _apply(self, fn, *args, **kwargs):      # .cuda() / .half() / .float() / .to()
-        self._lp_cache.engines.clear()
+        self._lp_cache.clear()
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
-        self._lp_cache.engines.clear()
+        self._lp_cache.clear()
         return super().load_state_dict(*args, **kwargs)
 
     def _load_from_state_dict(self, *args, **kwargs):   # when loaded as a child (network_to_half wrapper)
-        self._lp_cache.engines.clear()
+        self._lp_cache.clear()
         return super()._load_from_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        # training steps run the nn.Module tree and update parameters / BN statistics in place: the folded weights
+        # of a previous eval phase are stale afterwards
+        self._lp_cache.clear()
+        return super().train(mode)
+
+    def _lp_signature(self):
+        """Sum of the autograd version counters + identities of all parameters and buffers: changes with every
+        in-place update (optimizer.step, running statistics, .data.copy_/.mul_) and with every re-assignment."""
+        sig = 0
+        for t in self.parameters():
+            sig += t._version + (id(t) & 0xffff)
+        for t in self.buffers():
+            sig += t._version + (id(t) & 0xffff)
+        return sig
 
     def lp_engine(self, device=None):
         from litepose_b200.engine import LitePoseEngine
@@ -153,11 +179,17 @@ class LitePose(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("the litepose_b200 engine needs the module on a CUDA device")
         key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-        eng = self._lp_cache.engines.get(key)
-        if eng is None:
+        # DataParallel replicas receive freshly broadcast tensors on every forward (version 0, new identity): their
+        # engine is keyed by device only and lives until the master module invalidates the shared cache
+        replica = getattr(self, "_is_replica", False)
+        sig = None if replica else self._lp_signature()
+        with self._lp_cache.lock:
+            hit = self._lp_cache.engines.get(key)
+            if hit is not None and (replica or hit[1] is None or hit[1] == sig):
+                return hit[0]
             eng = LitePoseEngine(self.state_dict(), self.cfg_arch, torch.device("cuda", key[1]))
-            self._lp_cache.engines[key] = eng
-        return eng
+            self._lp_cache.engines[key] = (eng, sig)
+            return eng
 
     # -- forward -------------------------------------------------------------
     def _forward_modules(self, x):

@@ -73,6 +73,7 @@ class LitePosePipeline(object):
     def __init__(self, model, cfg, use_graphs=True, keep=64):
         """model: litepose_b200 drop-in LitePose on a CUDA device (eval)."""
         self.cfg = cfg
+        self._validate_cfg(cfg)
         self.lib = _lib.load()
         self.device = next(model.parameters()).device
         self.engine = model.lp_engine(self.device)
@@ -89,9 +90,34 @@ class LitePosePipeline(object):
         self.use_graphs = use_graphs
         import os
         self.two_streams = os.environ.get("LP_TWO_STREAMS", "1") != "0"
-        self.keep = keep                  # persons copied back per image in the fixed-size D2H payload
+        # persons per image in the fixed-size packed payload (the D2H copy / NCCL gather of every step).  The reference
+        # returns every person it finds (lib/core/group.py:96,269-291); an image with more than ``keep`` persons is
+        # never clipped: step() fetches the full result from the parser's buffers (capacity J*K persons) in a second
+        # copy, and unpack() raises if it is handed an overflowing payload without that second copy.
+        self.keep = min(int(keep), self.parser.pcap)
         self._state = {}
         self._final = None                # per-image inverse affines of get_final_preds (host, [N,6] float64)
+
+    @staticmethod
+    def _validate_cfg(cfg):
+        """The fused glue kernel implements the shipped evaluation settings (experiments/*/mobile.yaml on top of
+        lib/config/default.py); anything else is rejected here instead of being silently ignored
+        (reference lib/core/inference.py:75-208 branches on every one of these keys)."""
+        def bad(what):
+            raise NotImplementedError("LitePosePipeline: %s is not supported by the fused glue kernel "
+                                      "(use the reference's core.inference on the drop-in module instead)" % what)
+        if [float(v) for v in cfg.TEST.SCALE_FACTOR] != [1.0]:
+            bad("multi-scale test (TEST.SCALE_FACTOR=%r)" % (list(cfg.TEST.SCALE_FACTOR),))
+        if cfg.DATASET.WITH_CENTER:
+            bad("DATASET.WITH_CENTER")
+        if not cfg.MODEL.TAG_PER_JOINT:
+            bad("MODEL.TAG_PER_JOINT=False")
+        if tuple(cfg.LOSS.WITH_HEATMAPS_LOSS) != (True, True) or tuple(cfg.TEST.WITH_HEATMAPS) != (True, True):
+            bad("WITH_HEATMAPS_LOSS / TEST.WITH_HEATMAPS other than (True, True)")
+        if tuple(cfg.LOSS.WITH_AE_LOSS) != (True, False) or tuple(cfg.TEST.WITH_AE) != (True, False):
+            bad("WITH_AE_LOSS / TEST.WITH_AE other than (True, False)")
+        if int(cfg.LOSS.NUM_STAGES) != 2:
+            bad("LOSS.NUM_STAGES=%r" % (cfg.LOSS.NUM_STAGES,))
 
     def set_final_preds(self, centers=None, scales=None):
         """valid.py:230-233 on the device: after this call every step maps the keypoints of image i back to its original
@@ -142,6 +168,7 @@ class LitePosePipeline(object):
             _lib.check(self.lib.lp_transform_preds_f32(ans.data_ptr(), num.data_ptr(), st["trans"].data_ptr(), n,
                                                        ans.shape[1], ans.shape[2], ans.shape[3],
                                                        torch.cuda.current_stream().cuda_stream), "lp_transform_preds_f32")
+        st["full"] = (ans, num, scores)       # parser-owned buffers (capacity J*K persons), valid until the next step
         k = self.keep
         st["packed"][:, :k * st["row"]].copy_(ans[:, :k].reshape(n, -1))
         st["packed"][:, k * st["row"]:k * st["row"] + k].copy_(scores[:, :k])
@@ -164,12 +191,15 @@ class LitePosePipeline(object):
                 "tag": torch.empty((n, J, Hd, Wd, T), dtype=torch.float32, device=dev),
                 "packed": torch.zeros((n, self.keep * row + self.keep + 1), dtype=torch.float32, device=dev),
                 "host": torch.empty((n, self.keep * row + self.keep + 1), dtype=torch.float32).pin_memory(),
-                "row": row, "T": T, "graph": None, "plant": plant, "trans": None,
+                "row": row, "T": T, "graph": None, "plant": plant, "trans": None, "full": None,
             }
             if self._final is not None:
                 st["trans"] = torch.zeros((n, 6), dtype=torch.float64, device=dev)
             self._state[key] = st
-        st["plant"] = plant
+        if st["plant"] is not plant:
+            # a captured graph bakes the plant hook's index tensors in: a different hook (or none) needs a new capture
+            st["graph"] = None
+            st["plant"] = plant
         if st["trans"] is not None and st.get("trans_ver") != self._final_ver:
             if len(self._final[0]) != n:
                 raise ValueError("set_final_preds: %d centers for a batch of %d" % (len(self._final[0]), n))
@@ -205,18 +235,40 @@ class LitePosePipeline(object):
         st = self._get_state(n, x.shape[2], x.shape[3], x.dtype, plant)
         st["host"].copy_(packed, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.unpack(st["host"], st["row"], st["T"])
+        return self.unpack(st["host"], st["row"], st["T"], self.fetch_overflow(st, st["host"]))
 
-    def unpack(self, host, row, T):
-        """packed host tensor -> list over images of (ans ndarray [P,J,3+T], scores list), P clipped to keep."""
-        import numpy as np
+    def fetch_overflow(self, st, host):
+        """Second-chance copy for the images that found more than ``keep`` persons: {image index: (ans, scores)} read
+        from the parser's own buffers of the step that produced ``host`` (must be called before the next step)."""
+        counts = host[:, -1]
+        over = (counts > self.keep).nonzero().flatten().tolist()
+        if not over:
+            return None
+        ans, num, scores = st["full"]
+        out = {}
+        for i in over:
+            p = int(counts[i])
+            if p > ans.shape[1]:
+                raise _lib.LitePoseError("person capacity exceeded: %d > %d" % (p, ans.shape[1]))
+            out[i] = (ans[i, :p].cpu().numpy(), scores[i, :p].cpu().numpy())
+        return out
+
+    def unpack(self, host, row, T, overflow=None):
+        """packed host tensor -> list over images of (ans ndarray [P,J,3+T], scores list, P).  Every person is
+        returned: an image with P > keep needs its entry in ``overflow`` (fetch_overflow), else this raises."""
         a = host.numpy()
         J, k = self.params.num_joints, self.keep
         out = []
         for i in range(a.shape[0]):
             p = int(a[i, -1])
-            q = min(p, k)
-            ans = a[i, :k * row].reshape(k, J, 3 + T)[:q].copy()
-            sc = a[i, k * row:k * row + k][:q].copy()
+            if p > k:
+                if overflow is None or i not in overflow:
+                    raise _lib.LitePoseError("image %d holds %d persons but the packed payload carries %d: pass the "
+                                             "result of fetch_overflow() or raise keep" % (i, p, k))
+                ans, sc = overflow[i]
+                out.append((ans.copy(), list(sc), p))
+                continue
+            ans = a[i, :k * row].reshape(k, J, 3 + T)[:p].copy()
+            sc = a[i, k * row:k * row + k][:p].copy()
             out.append((ans, list(sc), p))
         return out

@@ -121,12 +121,17 @@ PARSER_CASES = [
     ("p12_256_t2", "crowd_pose", 256, 256, 2, 12, 5),
     ("p30_256_t1", "crowd_pose", 256, 256, 1, 30, 6),
     ("coco_p8_128_t2", "coco", 128, 160, 2, 8, 7),
+    # the bench geometries (BASELINE configs 3 and 5): 512^2 with 5 persons, 640^2 with a 30-person crowd
+    ("p5_512_t2", "crowd_pose", 512, 512, 2, 5, 8),
+    ("p30_640_t2", "crowd_pose", 640, 640, 2, 30, 9),
 ]
 
 
-def golden_parser():
+def golden_parser(only=None):
     ns = refshim.load()
     for name, ds, h, w, t, people, seed in PARSER_CASES:
+        if only and name not in only:
+            continue
         cfg = get_cfg(dataset=ds, input_size=256)
         nj = cfg.DATASET.NUM_JOINTS
         det, tag = synth.plant_crowd(nj, h, w, t, num_people=people, seed=seed)
@@ -171,9 +176,12 @@ def golden_munkres():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    golden_model()
-    golden_glue()
-    golden_parser()
-    golden_munkres()
+    if len(sys.argv) > 2 and sys.argv[1] == "--parser-only":       # regenerate selected parser cases only
+        golden_parser(only=set(sys.argv[2:]))
+    else:
+        golden_model()
+        golden_glue()
+        golden_parser()
+        golden_munkres()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

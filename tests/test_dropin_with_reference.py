@@ -47,3 +47,52 @@ def test_sys_path_shadowing():
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"ref": REF, "root": ROOT}], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0 and "dropin ok" in r.stdout, r.stdout + r.stderr
+
+
+CHECK = r'''
+import sys, types
+import _init_paths                                   # what valid.py:24 does: <reference>/lib to the FRONT of sys.path
+assert sys.path[0].endswith("lib"), sys.path[:3]
+from litepose_b200.config import FLIP_CONFIG
+ds = types.ModuleType("dataset"); dst = types.ModuleType("dataset.transforms"); dst.FLIP_CONFIG = FLIP_CONFIG
+ds.transforms = dst; sys.modules["dataset"] = ds; sys.modules["dataset.transforms"] = dst
+import models
+from core.group import HeatmapParser
+from core.inference import get_multi_stage_outputs
+from utils.transforms import get_final_preds
+import utils.zipreader
+repo = "%(root)s"
+assert models.pose_mobilenet.__file__.startswith(repo), models.pose_mobilenet.__file__
+assert sys.modules["core.group"].__file__.startswith(repo)
+assert sys.modules["utils.transforms"].__file__.startswith(repo)
+assert sys.modules["core.inference"].__file__.startswith("%(ref)s")
+assert utils.zipreader.__file__.startswith("%(ref)s")
+import models.pose_higher_hrnet as hr                # the rest of the model zoo still comes from the reference
+assert hr.__file__.startswith("%(ref)s")
+print("init_paths dropin ok")
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "lib", "core")), reason="reference tree not present")
+@pytest.mark.parametrize("how", ["sitecustomize", "runner"])
+def test_dropin_survives_init_paths(tmp_path, how):
+    """ADVICE r1: valid.py's `import _init_paths` inserts <reference>/lib at sys.path[0] AFTER PYTHONPATH /
+    sitecustomize, and <reference>/lib/models is a regular package - plain path shadowing loses and the model would
+    silently be the stock eager one.  The meta-path drop-in (litepose_b200/dropin.py) must win in both launch modes."""
+    script = tmp_path / "check_like_valid.py"
+    script.write_text(CHECK % {"ref": REF, "root": ROOT})
+    env = dict(os.environ)
+    if how == "sitecustomize":
+        env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "litepose_b200", "dropin_site"), ROOT])
+        # cwd = reference root so that `import _init_paths` resolves like for `python valid.py`
+        cmd = [sys.executable, "-c", "import sys; sys.path.insert(0, %r); exec(open(%r).read())" % (REF, str(script))]
+    else:
+        env["PYTHONPATH"] = ROOT
+        # the runner puts the script's directory first (as `python script.py` does); _init_paths lives beside valid.py
+        link = tmp_path / "ref"
+        os.symlink(REF, link)
+        runner_script = tmp_path / "run_in_ref.py"
+        runner_script.write_text("import sys; sys.path.insert(0, %r)\n" % REF + CHECK % {"ref": REF, "root": ROOT})
+        cmd = [sys.executable, "-m", "litepose_b200.dropin", str(runner_script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=REF)
+    assert r.returncode == 0 and "init_paths dropin ok" in r.stdout, r.stdout + r.stderr

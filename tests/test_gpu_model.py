@@ -119,6 +119,27 @@ def test_batch_independence_full_size():
     _tol(one[1].cpu().numpy(), ref[1].numpy(), "S512 out1")
 
 
+@pytest.mark.parametrize("name,size", [("M", 512), ("L", 640), ("XS", 448)])
+def test_baseline_config_archs_vs_oracle(name, size):
+    """BASELINE configs 2, 4 and 5 (LitePose-XS @448, -M @512, -L @640): one frame through the fp16 engine (plain and
+    mirrored pass) against the fp32 oracle forward (reference lib/models/pose_mobilenet.py:137-156)."""
+    cfg = get_cfg(input_size=size)
+    arch = get_arch(name)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, arch), 1).eval()
+    x = synth.make_frames(1, size, seed=21)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = model_ref.forward(sd, arch, x)
+        ref_f = model_ref.forward(sd, arch, torch.flip(x, [3]))
+    eng = model.cuda().lp_engine()
+    got = eng.run(x.cuda().half(), flip=False)
+    got_f = eng.run(x.cuda().half(), flip=True)
+    for i in range(2):
+        _tol(got[i].cpu().numpy(), ref[i].numpy(), "%s@%d out%d" % (name, size, i))
+        _tol(got_f[i].cpu().numpy(), ref_f[i].numpy(), "%s@%d flip out%d" % (name, size, i))
+
+
 @pytest.mark.parametrize("name,size", [("XS", 128), ("S", 128)])
 def test_shipped_arch_golden_fp16_rowsum_depthwise(golden_dir, name, size):
     """the packed-fp16 row-sum depthwise mode (lp_set_dw_precision(1)) must stay inside the same tolerance"""

@@ -6,6 +6,8 @@ import os
 
 import numpy as np
 import pytest
+
+from parity_util import assert_topk_equal
 import torch
 
 from litepose_b200 import _lib, synth
@@ -32,10 +34,7 @@ def test_parser_golden(golden_dir, case):
     p = _parser(cfg)
     dd, td = torch.from_numpy(det)[None].cuda(), torch.from_numpy(tag)[None].cuda()
     top = p.top_k(dd, td)
-    m = z["val_k"] > 0
-    assert np.array_equal(m, top["val_k"] > 0)
-    for k in ("val_k", "loc_k", "tag_k"):
-        assert np.array_equal(top[k][m], z[k][m]), k
+    assert_topk_equal(top, {k: z[k] for k in ("val_k", "loc_k", "tag_k")}, name)
     for adj, ref in ((True, True), (True, False), (False, False)):
         ans, scores = p.parse(dd, td, adj, ref)
         a = np.asarray(ans[0], dtype=np.float32).reshape(-1, nj, 3 + t)
@@ -178,3 +177,24 @@ def test_topk_dense_fallback():
     for k in ("val_k", "loc_k", "tag_k"):
         assert np.array_equal(top[k], exp[k]), k
     assert np.array_equal(top["loc_k"][0, 0, :, 0], np.arange(30)) and (top["loc_k"][0, 0, :, 1] == 0).all()
+
+
+@pytest.mark.parametrize("size,n,people,min_found", [(512, 4, 5, 5), (640, 2, 36, 65)])
+def test_parser_bench_geometry_vs_oracle(size, n, people, min_found):
+    """The parser at the geometry the bench runs it (BASELINE configs 3 and 5: 512^2 -> 8 strips per plane with the
+    cross-CTA threshold; 640^2 crowd with more persons than the 64-person packed payload), bit-exact against the
+    oracle for every person (reference lib/core/group.py:96,269-291 returns all of them)."""
+    cfg = get_cfg(input_size=size)
+    det, tag = synth.plant_crowd_batch(n, 14, size, size, 2, num_people=people, seed=300 + size)
+    p = _parser(cfg)
+    got = p.parse_batch(torch.from_numpy(det).cuda(), torch.from_numpy(tag).cuda(), True, True)
+    exp = group_ref.HeatmapParser(cfg).parse_batch(det.copy(), tag.copy(), True, True)
+    found = []
+    for i in range(n):
+        a = np.asarray(got[i][0][0], np.float32).reshape(-1, 14, 5)
+        e = np.asarray(exp[i][0][0], np.float32).reshape(-1, 14, 5)
+        assert a.shape == e.shape, (i, a.shape, e.shape)
+        assert np.array_equal(a, e), i
+        assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(exp[i][1], np.float32))
+        found.append(e.shape[0])
+    assert max(found) >= min_found, found

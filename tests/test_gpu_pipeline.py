@@ -1,0 +1,127 @@
+"""-m gpu: the public end-to-end call (LitePosePipeline.step: pinned host frames -> keypoints on the host) on the bench
+workload, against the oracle pipeline the bench times as its CPU arm (bench.py:cpu_reference_step = reference
+valid.py:195-229: two forwards with flip, glue, parser per image)."""
+import numpy as np
+import pytest
+import torch
+
+from litepose_b200 import _lib, synth
+from litepose_b200.config import get_arch, get_cfg
+from litepose_b200.lib.models.pose_mobilenet import get_pose_net
+from litepose_b200.pipeline import LitePosePipeline, PlantedCrowd
+from oracle import group_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(arch_name, size, n, people, keep=64, seed=77):
+    cfg = get_cfg(input_size=size)
+    arch = get_arch(arch_name)
+    torch.manual_seed(0)
+    model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, arch), 1)).eval()
+    sd = {k: v.float().clone() for k, v in model.state_dict().items()}
+    frames = synth.make_frames(n, size, seed=1234)
+    pipe = LitePosePipeline(model.cuda(), cfg, use_graphs=True, keep=keep)
+    plant_dev = PlantedCrowd(n, 14, size, size, 2, num_people=people, seed=seed, device="cuda")
+    plant_cpu = PlantedCrowd(n, 14, size, size, 2, num_people=people, seed=seed, device="cpu")
+    return cfg, arch, sd, frames, pipe, plant_dev, plant_cpu
+
+
+def test_step_vs_oracle_pipeline_s512():
+    """BASELINE config 3 geometry (LitePose-S 512^2, flip test, PROJECT2IMAGE, adjust + refine), batch 2."""
+    import bench
+    n, size = 2, 512
+    cfg, arch, sd, frames, pipe, plant_dev, plant_cpu = _setup("S", size, n, 5)
+    got = pipe.step(frames.half().pin_memory(), plant_dev)
+    got2 = pipe.step(frames.half().pin_memory(), plant_dev)            # graph replay
+    st = pipe._get_state(n, size, size, torch.float16, plant_dev)
+    det_g, tag_g = st["det"].cpu().numpy(), st["tag"].cpu().numpy()
+
+    # (1) the maps the device parser saw == glue(oracle forward) + plant within the fp tolerance of the model
+    from oracle import glue_ref, model_ref
+    with torch.no_grad():
+        _, hm, tg = glue_ref.multi_stage_outputs(cfg, lambda im: model_ref.forward(sd, arch, im), frames, True, True,
+                                                 (size, size))
+        det_o, tag_o = glue_ref.aggregate(cfg, hm, tg)
+        det_o, tag_o = det_o.contiguous(), tag_o.contiguous()
+        det_raw, tag_raw = det_o.clone(), tag_o.clone()
+        plant_cpu.apply(det_o, tag_o)
+    for name, g, o, raw in (("det", det_g, det_o.numpy(), det_raw.numpy()), ("tag", tag_g, tag_o.numpy(), tag_raw.numpy())):
+        err = np.abs(g - o).max()
+        lim = 2e-3 * np.abs(raw).max() + 1e-4          # tolerance relative to the NETWORK's maps, not the planted peaks
+        assert err <= lim, "%s: %.3e > %.3e" % (name, err, lim)
+
+    # (2) the packed result of the step is bit-exactly the oracle parser's answer on the maps the device produced
+    op = group_ref.HeatmapParser(cfg)
+    for i in range(n):
+        ans, scores = op.parse(det_g[i:i + 1].copy(), tag_g[i:i + 1].copy(), True, True)
+        e = np.asarray(ans[0], np.float32).reshape(-1, 14, 5)
+        for res in (got, got2):
+            assert res[i][2] == e.shape[0]
+            assert np.array_equal(res[i][0], e), i
+            assert np.array_equal(np.asarray(res[i][1], np.float32), np.asarray(scores, np.float32))
+
+    # (3) against the full CPU oracle pipeline (fp32 forward): same person count, same integer peak locations and
+    # adjusted coordinates for every joint the matcher assigned (tag columns non-zero), values / tags within tolerance.
+    # Joints filled in by refine on planes where the person has no planted peak are an argmax over network noise and
+    # are compared through (2) only.
+    exp = bench.cpu_reference_step(cfg, arch, sd, frames, plant_cpu)
+    for i in range(n):
+        e = np.asarray(exp[i][0][0], np.float32).reshape(-1, 14, 5)
+        a = got[i][0]
+        assert a.shape == e.shape, (i, a.shape, e.shape)
+        matched = (e[:, :, 3] != 0) | (e[:, :, 4] != 0)
+        assert np.array_equal(matched, (a[:, :, 3] != 0) | (a[:, :, 4] != 0))
+        assert matched.sum() >= 5 * 10
+        assert np.array_equal(a[matched][:, :2], e[matched][:, :2]), "peak locations"
+        assert np.abs(a[matched][:, 2:] - e[matched][:, 2:]).max() <= 2e-3 * np.abs(e[matched][:, 2:]).max() + 1e-4
+
+
+def test_crowd_overflow_returns_every_person():
+    """BASELINE config 5 geometry (LitePose-L 640^2, 30-person planted crowd): more persons than the 64-person packed
+    payload -> the step still returns all of them (reference lib/core/group.py:96 keeps every person), equal to the
+    oracle parser on the same maps; unpack() without the second-chance copy raises instead of clipping."""
+    n, size = 2, 640
+    cfg, arch, sd, frames, pipe, plant_dev, _ = _setup("L", size, n, 30, keep=24, seed=78)
+    got = pipe.step(frames.half().pin_memory(), plant_dev)
+    st = pipe._get_state(n, size, size, torch.float16, plant_dev)
+    det_g, tag_g = st["det"].cpu().numpy(), st["tag"].cpu().numpy()
+    op = group_ref.HeatmapParser(cfg)
+    counts = []
+    for i in range(n):
+        ans, scores = op.parse(det_g[i:i + 1].copy(), tag_g[i:i + 1].copy(), True, True)
+        e = np.asarray(ans[0], np.float32).reshape(-1, 14, 5)
+        counts.append(e.shape[0])
+        assert got[i][2] == e.shape[0] and got[i][0].shape == e.shape
+        assert np.array_equal(got[i][0], e)
+        assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(scores, np.float32))
+    assert max(counts) > 24, counts
+    with pytest.raises(_lib.LitePoseError):
+        pipe.unpack(st["host"], st["row"], st["T"])
+
+
+def test_unsupported_cfg_is_rejected():
+    cfg = get_cfg(input_size=128)
+    torch.manual_seed(0)
+    model = get_pose_net(cfg, False, get_arch("XS")).eval().cuda()
+    for mutate in (lambda c: setattr(c.TEST, "SCALE_FACTOR", [0.5, 1, 2]), lambda c: setattr(c.DATASET, "WITH_CENTER", True),
+                   lambda c: setattr(c.TEST, "WITH_AE", (True, True))):
+        c = get_cfg(input_size=128)
+        mutate(c)
+        with pytest.raises(NotImplementedError):
+            LitePosePipeline(model, c)
+
+
+def test_plant_change_recaptures_graph():
+    """a captured step graph must not keep replaying the first call's plant hook."""
+    n, size = 2, 128
+    cfg, arch, sd, frames, pipe, plant_a, _ = _setup("XS", size, n, 3, seed=5)
+    plant_b = PlantedCrowd(n, 14, size, size, 2, num_people=2, seed=6, device="cuda")
+    fr = frames.half().pin_memory()
+    a1 = pipe.step(fr, plant_a)
+    b = pipe.step(fr, plant_b)
+    none = pipe.step(fr, None)
+    a2 = pipe.step(fr, plant_a)
+    assert [r[2] for r in none] == [0, 0]
+    assert [r[2] for r in a1] == [r[2] for r in a2] and all(np.array_equal(x[0], y[0]) for x, y in zip(a1, a2))
+    assert [r[2] for r in b] != [r[2] for r in a1] or not np.array_equal(a1[0][0], b[0][0])

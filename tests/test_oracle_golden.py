@@ -6,6 +6,8 @@ import os
 
 import numpy as np
 import pytest
+
+from parity_util import assert_topk_equal
 import torch
 
 from litepose_b200 import synth
@@ -89,10 +91,7 @@ def test_parser(golden_dir, case):
     assert hashlib.sha256(det.tobytes() + tag.tobytes()).hexdigest() == str(z["in_digest"])
     p = group_ref.HeatmapParser(cfg)
     top = p.top_k(det[None], tag[None])
-    m = z["val_k"] > 0
-    assert np.array_equal(m, top["val_k"] > 0)
-    for k in ("val_k", "loc_k", "tag_k"):
-        assert np.array_equal(top[k][m], z[k][m]), k
+    assert_topk_equal(top, {k: z[k] for k in ("val_k", "loc_k", "tag_k")}, name)
     for adj, ref in ((True, True), (True, False), (False, False)):
         ans, scores = p.parse(det[None].copy(), tag[None].copy(), adj, ref)
         a = np.array(ans[0], dtype=np.float32).reshape(-1, nj, 3 + t)
