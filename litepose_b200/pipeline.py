@@ -96,6 +96,7 @@ class LitePosePipeline(object):
         # copy, and unpack() raises if it is handed an overflowing payload without that second copy.
         self.keep = min(int(keep), self.parser.pcap)
         self._state = {}
+        self._async = None                # submit()/collect() slots
         self._final = None                # per-image inverse affines of get_final_preds (host, [N,6] float64)
 
     @staticmethod
@@ -236,6 +237,87 @@ class LitePosePipeline(object):
         st["host"].copy_(packed, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.unpack(st["host"], st["row"], st["T"], self.fetch_overflow(st, st["host"]))
+
+    # -- asynchronous end-to-end API: two steps in flight -----------------------------------------
+    def submit(self, frames_pinned, plant=None, group=None, dst=0):
+        """Enqueue one end-to-end step and return a ticket; ``collect(ticket)`` blocks until that step's keypoints are
+        on the host.  Nothing here synchronises the host: the pinned->device copy of the frames runs on a copy stream,
+        the step on the current stream, and the packed result leaves through one of two result slots on a result
+        stream (D2H of step i overlaps the compute of step i+1; with ``group`` - a torch.distributed process group of
+        one rank per GPU - the slot is first gathered on rank ``dst`` with ONE NCCL gather and leaves that rank in
+        ONE device->host copy).  At most two tickets may be outstanding.  An image with more persons than ``keep``
+        makes collect() raise (never clipped): use the blocking step(), or a larger ``keep``."""
+        import torch.distributed as dist
+        n, _, s_h, s_w = frames_pinned.shape
+        main = torch.cuda.current_stream()
+        a = self._async
+        if a is None or a["key"] != (n, s_h, s_w, frames_pinned.dtype, id(group)):
+            world = dist.get_world_size(group) if group is not None else 1
+            rank = dist.get_rank(group) if group is not None else 0
+            st = self._get_state(n, s_h, s_w, frames_pinned.dtype, plant)
+            width = st["packed"].shape[1]
+            slots = []
+            for _ in range(2):
+                sl = {"x": torch.empty((n, 3, s_h, s_w), dtype=frames_pinned.dtype, device=self.device),
+                      "out": torch.empty((n, width), dtype=torch.float32, device=self.device),
+                      "step_done": None, "d2h_done": None, "busy": False}
+                if world > 1 and rank == dst:
+                    sl["all"] = torch.empty((world, n, width), dtype=torch.float32, device=self.device)
+                sl["host"] = torch.empty((world if rank == dst else 1, n, width), dtype=torch.float32).pin_memory()
+                slots.append(sl)
+            a = self._async = {"key": (n, s_h, s_w, frames_pinned.dtype, id(group)), "slots": slots, "next": 0,
+                               "copy": torch.cuda.Stream(device=self.device), "res": torch.cuda.Stream(device=self.device),
+                               "world": world, "rank": rank, "dst": dst, "group": group, "row": st["row"], "T": st["T"]}
+        i = a["next"]
+        sl = a["slots"][i]
+        if sl["busy"]:
+            raise RuntimeError("LitePosePipeline.submit: two steps are already in flight - collect() one first")
+        a["next"] = i ^ 1
+        with torch.cuda.stream(a["copy"]):
+            if sl["step_done"] is not None:
+                a["copy"].wait_event(sl["step_done"])        # the step that last read this input slot
+            sl["x"].copy_(frames_pinned, non_blocking=True)
+            h2d = torch.cuda.Event()
+            h2d.record(a["copy"])
+        main.wait_event(h2d)
+        if sl["d2h_done"] is not None:
+            main.wait_event(sl["d2h_done"])                  # the result slot is free again
+        packed = self.step_device(sl["x"], plant)
+        sl["out"].copy_(packed, non_blocking=True)
+        sl["step_done"] = torch.cuda.Event()
+        sl["step_done"].record(main)
+        with torch.cuda.stream(a["res"]):
+            a["res"].wait_event(sl["step_done"])
+            if a["world"] > 1:
+                glist = list(sl["all"].unbind(0)) if a["rank"] == a["dst"] else None
+                dist.gather(sl["out"], glist, dst=a["dst"], group=group)
+                if a["rank"] == a["dst"]:
+                    sl["host"].copy_(sl["all"], non_blocking=True)
+            else:
+                sl["host"][0].copy_(sl["out"], non_blocking=True)
+            sl["d2h_done"] = torch.cuda.Event()
+            sl["d2h_done"].record(a["res"])
+        sl["busy"] = True
+        return i
+
+    def collect(self, ticket, unpack=True):
+        """Wait for the step behind ``ticket``.  Returns, per rank of the group (one entry without a group), the list
+        over images of (ans [P,J,3+T], scores, P); on ranks other than ``dst`` of a group: None.  With unpack=False the
+        pinned host tensor [ranks, N, width] itself is returned."""
+        a = self._async
+        sl = a["slots"][ticket]
+        if not sl["busy"]:
+            raise RuntimeError("LitePosePipeline.collect: ticket %r is not in flight" % (ticket,))
+        sl["d2h_done"].synchronize()
+        sl["busy"] = False
+        if a["world"] > 1 and a["rank"] != a["dst"]:
+            return None
+        if float(sl["host"][:, :, -1].max()) > self.keep:
+            raise _lib.LitePoseError("an image holds more persons than the packed payload carries (%d): use step() or "
+                                     "a larger keep" % self.keep)
+        if not unpack:
+            return sl["host"]
+        return [self.unpack(sl["host"][r], a["row"], a["T"]) for r in range(sl["host"].shape[0])]
 
     def fetch_overflow(self, st, host):
         """Second-chance copy for the images that found more than ``keep`` persons: {image index: (ans, scores)} read

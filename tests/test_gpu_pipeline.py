@@ -125,3 +125,28 @@ def test_plant_change_recaptures_graph():
     assert [r[2] for r in none] == [0, 0]
     assert [r[2] for r in a1] == [r[2] for r in a2] and all(np.array_equal(x[0], y[0]) for x, y in zip(a1, a2))
     assert [r[2] for r in b] != [r[2] for r in a1] or not np.array_equal(a1[0][0], b[0][0])
+
+
+def test_submit_collect_equals_step():
+    """The asynchronous API (two steps in flight, result slots, no per-step synchronisation) returns exactly what the
+    blocking step() returns, in submission order, also when the inputs alternate."""
+    n, size = 2, 128
+    cfg, arch, sd, frames, pipe, plant, _ = _setup("XS", size, n, 3, seed=5)
+    fa = frames.half().pin_memory()
+    fb = synth.make_frames(n, size, seed=99).half().pin_memory()
+    ref_a, ref_b = pipe.step(fa, plant), pipe.step(fb, plant)
+    seq = [fa, fb, fb, fa, fa, fb]
+    exp = [ref_a, ref_b, ref_b, ref_a, ref_a, ref_b]
+    got, prev = [], None
+    for f in seq:
+        t = pipe.submit(f, plant)
+        if prev is not None:
+            got.append(pipe.collect(prev)[0])
+        prev = t
+    got.append(pipe.collect(prev)[0])
+    with pytest.raises(RuntimeError):
+        pipe.collect(prev)
+    for g, e in zip(got, exp):
+        assert [r[2] for r in g] == [r[2] for r in e]
+        for x, y in zip(g, e):
+            assert np.array_equal(x[0], y[0]) and np.array_equal(np.asarray(x[1]), np.asarray(y[1]))
