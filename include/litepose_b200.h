@@ -104,6 +104,20 @@ int lp_dw7_project_f16(const void* x, const void* w_dw, const float* b_dw, const
                        const float* b_proj_packed, const void* residual, void* out, int N, int H, int W,
                        int Ce, int Co, lp_stream_t stream);
 
+/* ---- M2 block-fused: one stride-1 InvBottleneck in ONE kernel ---------------------------------
+ * reference lib/models/layers/layers.py:90-118 (inv -> depth_conv -> point_conv -> + identity).  The narrow haloed
+ * input tile is expanded on the tensor cores inside the kernel; the 6x tensor never reaches HBM.
+ * x [N,H,W,Cin] fp16 NHWC; w_exp_packed from lp_block_s1_pack_wexp ([Ce][Cin] BN-folded); b_exp [Ce];
+ * w_dw tap-major [49][Ce]; b_dw [Ce]; w_proj_packed / b_proj_packed from lp_pw1x1_pack(K = Ce, N = Co);
+ * identity != 0 adds x (Cin == Co).  Shapes the kernel can hold on chip: lp_block_s1_supported() (Cin <= 64, Co <= 64,
+ * shared-memory budget on Ce); callers fall back to lp_pw1x1_f16 + lp_dw7_project_f16 otherwise. */
+int lp_block_s1_supported(int Cin, int Ce, int Co);
+size_t lp_block_s1_wexp_elems(int Cin, int Ce);     /* fp16 elements */
+int lp_block_s1_pack_wexp(const uint16_t* w_f16 /*[Ce][Cin] host*/, int Cin, int Ce, uint16_t* out /*host*/);
+int lp_block_s1_f16(const void* x, const void* w_exp_packed, const float* b_exp, const void* w_dw, const float* b_dw,
+                    const void* w_proj_packed, const float* b_proj_packed, int identity, void* out, int N, int H, int W,
+                    int Cin, int Ce, int Co, lp_stream_t stream);
+
 /* ---- M3: fusion deconv level ----------------------------------------------
  * out = ReLU(ConvT4x4s2p1(refined) + ConvT4x4s2p1(raw) + bias), one kernel.
  * refined NHWC fp16 [N,H,W,Cr], raw [N,H,W,Cw], out [N,2H,2W,Co].

@@ -58,6 +58,7 @@ class LitePoseEngine(object):
         import os
         self.fuse_dw_project = os.environ.get("LP_FUSE_DW_PROJECT", "1") != "0"
         self.fuse_heads = os.environ.get("LP_FUSE_HEADS", "1") != "0"
+        self.fuse_block = os.environ.get("LP_FUSE_BLOCK", "1") != "0"
 
     # ------------------------------------------------------------------ folded checkpoint ("next" row 4)
     # BN fold (reference fuse_bn.py:81-162) and kernel packing become a load-time no-op: the file holds exactly the
@@ -178,6 +179,15 @@ class LitePoseEngine(object):
                 s, b = _fold(sd, p + "point_conv.1")
                 pc = self._pack_pw(sd[p + "point_conv.0.weight"].float() * s.view(-1, 1, 1, 1), b)
                 cin, cout = inv["K"], pc["N"]
+                if stride == 1 and dw["k"] == 7 and self.lib.lp_block_s1_supported(cin, inv["N"], cout):
+                    # block-fused kernel: expansion weights as [Ce][Cin padded to 64] K-major rows, fp32 bias
+                    wfold = sd[p + "inv.0.weight"].float() * _fold(sd, p + "inv.1")[0].view(-1, 1, 1, 1)
+                    w16 = _np16(wfold.reshape(inv["N"], cin))
+                    wk = np.zeros(self.lib.lp_block_s1_wexp_elems(cin, inv["N"]), np.uint16)
+                    _lib.check(self.lib.lp_block_s1_pack_wexp(w16.ctypes.data, cin, inv["N"], wk.ctypes.data),
+                               "lp_block_s1_pack_wexp")
+                    inv["wblk"] = self._dev(wk, torch.float16)
+                    inv["bblk"] = _fold(sd, p + "inv.1")[1].float().contiguous().to(self.device)
                 blocks.append({"inv": inv, "dw": dw, "pc": pc, "stride": stride, "stage": si,
                                "res": stride == 1 and cin == cout, "last": bi == st["num_blocks"] - 1})
             self.channels.append(blocks[-1]["pc"]["N"])
@@ -271,11 +281,21 @@ class LitePoseEngine(object):
         for blk in P["blocks"]:
             inv, dw, pc = blk["inv"], blk["dw"], blk["pc"]
             oh, ow = ch // blk["stride"], cw_ // blk["stride"]
+            out = buf(n, oh, ow, pc["N"])
+            keep.append(out)
+            if self.fuse_block and self.fuse_dw_project and "wblk" in inv:
+                # the whole block in one kernel: the 6x-expanded tensor never reaches HBM
+                ops.append(_Op("block_s1", lib.lp_block_s1_f16,
+                               [cur.data_ptr(), inv["wblk"].data_ptr(), inv["bblk"].data_ptr(), dw["w"].data_ptr(),
+                                dw["b"].data_ptr(), pc["w"].data_ptr(), pc["b"].data_ptr(), 1 if blk["res"] else 0,
+                                out.data_ptr(), n, ch, cw_, inv["K"], dw["C"], pc["N"]]))
+                cur, ch, cw_ = out, oh, ow
+                if blk["last"]:
+                    x_list.append((cur, ch, cw_))
+                continue
             ops.append(_Op("inv", lib.lp_pw1x1_f16, [cur.data_ptr(), inv["w"].data_ptr(), inv["b"].data_ptr(), None,
                                                       e_buf.data_ptr(), n * ch * cw_, inv["K"], inv["N"],
                                                       _lib.ACT_RELU6]))
-            out = buf(n, oh, ow, pc["N"])
-            keep.append(out)
             if self.fuse_dw_project and blk["stride"] == 1 and dw["k"] == 7 and pc["N"] <= 160 and dw["C"] <= 992:
                 # depthwise + projection (+ identity) in one kernel: the expanded dw output never reaches HBM
                 ops.append(_Op("dw7_project", lib.lp_dw7_project_f16,

@@ -234,3 +234,57 @@ def test_head_fused(n, h, w, c1, c2, co, fp32):
                                      out.data_ptr(), 1 if fp32 else 0, n, h, w, c1, c2, co, stream()), "head_fused")
     torch.cuda.synchronize()
     tol_check(out, ref, what="head_fused c1 %d c2 %d co %d" % (c1, c2, co))
+
+
+@pytest.mark.parametrize("n,h,w,cin,ce,co,res", [
+    (1, 16, 16, 16, 96, 16, True), (2, 32, 32, 16, 96, 16, True), (1, 32, 48, 32, 192, 32, True),
+    (2, 20, 36, 24, 144, 24, True),            # ragged tiles, K padded 24 -> 32
+    (1, 16, 16, 16, 32, 16, False),            # a single slab
+    (1, 32, 32, 32, 64, 48, False),            # two slabs, no identity
+    (1, 16, 16, 64, 160, 64, True),            # widest supported input / output
+    # more tiles than SMs: several tiles per persistent CTA (X buffer hand-over, slot phases across tiles)
+    (8, 128, 128, 16, 96, 16, True), (6, 80, 96, 32, 192, 32, True), (3, 112, 112, 24, 144, 24, True),
+])
+def test_block_s1_fused(n, h, w, cin, ce, co, res):
+    """whole stride-1 InvBottleneck in one kernel (expand on tensor cores -> slab -> depthwise -> projection -> identity)
+    against the unfused fp32 reference with fp16 storage of the two intermediates (what the unfused kernels compute)"""
+    lib = _lib.load()
+    assert lib.lp_block_s1_supported(cin, ce, co) == 1
+    g = torch.Generator().manual_seed(cin * 3 + ce + co + h)
+    x = q16(torch.randn(n, cin, h, w, generator=g))
+    we = q16(torch.randn(ce, cin, generator=g) / (cin ** 0.5))
+    be = torch.randn(ce, generator=g) * 0.2
+    wd = q16(torch.randn(ce, 1, 7, 7, generator=g) * 0.1)
+    bd = torch.randn(ce, generator=g) * 0.1
+    wp = q16(torch.randn(co, ce, generator=g) / (ce ** 0.5))
+    bp = torch.randn(co, generator=g) * 0.1
+    e = q16(F.relu6(F.conv2d(x, we.view(ce, cin, 1, 1), be)))
+    mid = q16(F.relu6(F.conv2d(e, wd, bd, 1, 3, 1, ce)))
+    ref = F.conv2d(mid, wp.view(co, ce, 1, 1), bp)
+    if res:
+        ref = ref + x
+    wpk, bpk = pack_pw(wp, bp)
+    we16 = np.ascontiguousarray(we.half().numpy()).view(np.uint16)
+    wek = np.zeros(lib.lp_block_s1_wexp_elems(cin, ce), np.uint16)
+    _lib.check(lib.lp_block_s1_pack_wexp(we16.ctypes.data, cin, ce, wek.ctypes.data))
+    wed = torch.from_numpy(wek).view(torch.float16).cuda()
+    xd = nhwc16(x)
+    wdd = wd.reshape(ce, 49).t().contiguous().half().cuda()
+    out = torch.full((n, h, w, co), float("nan"), dtype=torch.float16, device="cuda")
+    bed, bdd = be.cuda(), bd.cuda()      # keep the device copies alive (two temporaries would alias in the allocator)
+    for _ in range(2):       # second launch: no state leaks between launches
+        _lib.check(lib.lp_block_s1_f16(xd.data_ptr(), wed.data_ptr(), bed.data_ptr(), wdd.data_ptr(),
+                                       bdd.data_ptr(), wpk.data_ptr(), bpk.data_ptr(), 1 if res else 0,
+                                       out.data_ptr(), n, h, w, cin, ce, co, stream()), "block_s1")
+    torch.cuda.synchronize()
+    tol_check(from_nhwc(out), ref, what="block_s1 cin%d ce%d co%d" % (cin, ce, co))
+
+
+def test_block_s1_unsupported_shapes():
+    lib = _lib.load()
+    assert lib.lp_block_s1_supported(48, 288, 48) == 0      # shared-memory budget
+    assert lib.lp_block_s1_supported(120, 720, 120) == 0    # Cin > 64
+    x = torch.zeros(1, 16, 16, 120, dtype=torch.float16, device="cuda")
+    rc = lib.lp_block_s1_f16(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), None, x.data_ptr(), None, 0, x.data_ptr(),
+                             1, 16, 16, 120, 720, 120, stream())
+    assert rc != 0 and b"unsupported shape" in lib.lp_last_error()
