@@ -15,6 +15,8 @@
 //     stores.
 // Warp roles: 0-15 depthwise (two groups of 8 = even / odd 32-channel slabs), 16 TMA producer, 17 MMA issuer.
 // HBM traffic of a block: read N*H*W*Cin*2 (x1.9 halo, L2 hits) + identity row, write N*H*W*Co*2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dw_inner.cuh"
 
@@ -54,6 +56,7 @@ struct BkParams {
     int tiles_x, tiles_y, num_tiles;
     int nslabs, nkb, k16;             // k16 = K=16 MMA steps that carry input channels (ceil(Cin/16))
     int off_we, off_slab, off_dww, off_a, off_wp, off_bias;   // shared-memory layout (bytes)
+    int skew_ns;                      // group 1 starts every tile this much later (phase offset of the two groups)
     const float* b_exp;               // [Ce]
     const float* b_dw;                // [Ce]
     const float* b_pj;                // packed, n_tile
@@ -215,6 +218,7 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         pdl_wait();                                        // the identity rows are read from global memory
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
+            if (grp && p.skew_ns) __nanosleep(p.skew_ns);
             // which of this thread's 4 expansion rows (haloed pixels) lie inside the image
             uint32_t inside = 0;
 #pragma unroll
@@ -426,6 +430,14 @@ extern "C" int lp_block_s1_f16(const void* x, const void* w_exp_packed, const fl
     p.b_dw = b_dw;
     p.b_pj = b_proj_packed;
     p.residual = identity ? reinterpret_cast<const __half*>(x) : nullptr;
+    {
+        static int skew = -1;
+        if (skew < 0) {
+            const char* e = getenv("LP_BLOCK_SKEW_NS");
+            skew = e ? atoi(e) : 0;
+        }
+        p.skew_ns = skew;
+    }
     p.out = reinterpret_cast<__half*>(out);
     CUtensorMap mx, mwe, mdw, mwp;
     {

@@ -139,7 +139,8 @@ class LitePosePipeline(object):
             for c, s in zip(*self._final)]).reshape(-1, 6))
 
     # -- device step (everything between the H2D copy and the D2H copy) -------------
-    def _device_step(self, st, x):
+    def _forward_part(self, st, x, det, tag):
+        """Both network passes + fused glue (+ the benchmark's planted persons) -> det / tag of this step."""
         eng, J = self.engine, self.params.num_joints
         if self.flip and self.two_streams:
             # the plain and the mirrored pass are independent until the glue: fork onto a side stream so that one pass'
@@ -157,24 +158,86 @@ class LitePosePipeline(object):
                 f = eng.run(x, flip=True, out_fp32=True, clone=False)
         o0, o1 = o[0], o[1]
         n, _, h, w = o0.shape
-        Hd, Wd = st["det"].shape[2], st["det"].shape[3]
+        Hd, Wd = det.shape[2], det.shape[3]
         _lib.check(self.lib.lp_glue_f32(o0.data_ptr(), o1.data_ptr(), f[0].data_ptr() if self.flip else None,
                                         f[1].data_ptr() if self.flip else None, self.fidx.data_ptr(), n, J, h, w,
-                                        1 if self.flip else 0, Hd, Wd, st["det"].data_ptr(), st["tag"].data_ptr(),
+                                        1 if self.flip else 0, Hd, Wd, det.data_ptr(), tag.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream), "lp_glue_f32")
         if st["plant"] is not None:
-            st["plant"].apply(st["det"], st["tag"])
-        ans, num, scores = self.parser.run(st["det"], st["tag"], self.adjust, self.refine)
+            st["plant"].apply(det, tag)
+
+    def _parser_part(self, st, det, tag, packed):
+        """Device parser (+ get_final_preds) on det / tag -> packed fixed-size payload."""
+        n = det.shape[0]
+        ans, num, scores = self.parser.run(det, tag, self.adjust, self.refine)
         if st["trans"] is not None:
             _lib.check(self.lib.lp_transform_preds_f32(ans.data_ptr(), num.data_ptr(), st["trans"].data_ptr(), n,
                                                        ans.shape[1], ans.shape[2], ans.shape[3],
                                                        torch.cuda.current_stream().cuda_stream), "lp_transform_preds_f32")
         st["full"] = (ans, num, scores)       # parser-owned buffers (capacity J*K persons), valid until the next step
         k = self.keep
-        st["packed"][:, :k * st["row"]].copy_(ans[:, :k].reshape(n, -1))
-        st["packed"][:, k * st["row"]:k * st["row"] + k].copy_(scores[:, :k])
-        st["packed"][:, -1].copy_(num.float())
-        return st["packed"]
+        packed[:, :k * st["row"]].copy_(ans[:, :k].reshape(n, -1))
+        packed[:, k * st["row"]:k * st["row"] + k].copy_(scores[:, :k])
+        packed[:, -1].copy_(num.float())
+        return packed
+
+    # -- device step (everything between the H2D copy and the D2H copy) -------------
+    def _device_step(self, st, x):
+        self._forward_part(st, x, st["det"], st["tag"])
+        return self._parser_part(st, st["det"], st["tag"], st["packed"])
+
+    def step_device_overlapped(self, x_dev, plant=None):
+        """Throughput form of step_device: the network passes + glue of this step run on the current stream while the
+        parser of the PREVIOUS step is still running on a second stream (the parser is a chain of short, latency-bound
+        kernels - one warp per image in the matcher - that leave most of the GPU idle; det / tag / packed are double
+        buffered).  Returns (packed, event): ``packed`` is valid once ``event`` has completed, and stays valid until the
+        second next call.  CUDA graphs only."""
+        if not self.use_graphs:
+            raise RuntimeError("step_device_overlapped needs use_graphs=True")
+        n, _, s_h, s_w = x_dev.shape
+        st = self._get_state(n, s_h, s_w, x_dev.dtype, plant)
+        ov = st.get("ov")
+        if ov is None:
+            ov = st["ov"] = {"det": [st["det"], torch.empty_like(st["det"])], "tag": [st["tag"], torch.empty_like(st["tag"])],
+                             "packed": [st["packed"], torch.zeros_like(st["packed"])], "gF": [None, None], "gP": [None, None],
+                             "pstream": torch.cuda.Stream(device=self.device), "P_done": [None, None],
+                             "consumer_done": [None, None], "idx": 0}
+        if st["graph"] is None and ov["gF"][0] is not None and st.get("ov_plant") is not plant:
+            ov["gF"] = [None, None]               # the plant hook changed: re-capture the forward graphs
+        st["ov_plant"] = plant
+        b = ov["idx"]
+        ov["idx"] = b ^ 1
+        main = torch.cuda.current_stream()
+        ps = ov["pstream"]
+        if ov["P_done"][b] is not None:
+            main.wait_event(ov["P_done"][b])      # the parser that last read det/tag[b] has finished
+        st["x"].copy_(x_dev, non_blocking=True)
+        if ov["gF"][b] is None:
+            self.engine.use_graphs = False
+            self._forward_part(st, st["x"], ov["det"][b], ov["tag"][b])      # warm-up: builds plans, sets attributes
+            self._parser_part(st, ov["det"][b], ov["tag"][b], ov["packed"][b])
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._forward_part(st, st["x"], ov["det"][b], ov["tag"][b])
+            ov["gF"][b] = g
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._parser_part(st, ov["det"][b], ov["tag"][b], ov["packed"][b])
+            ov["gP"][b] = g
+        ov["gF"][b].replay()
+        f_done = torch.cuda.Event()
+        f_done.record(main)
+        with torch.cuda.stream(ps):
+            ps.wait_event(f_done)
+            if ov["consumer_done"][b] is not None:
+                ps.wait_event(ov["consumer_done"][b])     # the previous payload of this slot has been copied out
+            ov["gP"][b].replay()
+            ev = torch.cuda.Event()
+            ev.record(ps)
+        ov["P_done"][b] = ev
+        st["ov_last"] = b
+        return ov["packed"][b], ev
 
     def _get_state(self, n, s_h, s_w, dtype, plant):
         key = (n, s_h, s_w, dtype, self._final is not None)
@@ -192,7 +255,7 @@ class LitePosePipeline(object):
                 "tag": torch.empty((n, J, Hd, Wd, T), dtype=torch.float32, device=dev),
                 "packed": torch.zeros((n, self.keep * row + self.keep + 1), dtype=torch.float32, device=dev),
                 "host": torch.empty((n, self.keep * row + self.keep + 1), dtype=torch.float32).pin_memory(),
-                "row": row, "T": T, "graph": None, "plant": plant, "trans": None, "full": None,
+                "row": row, "T": T, "graph": None, "plant": plant, "trans": None, "full": None, "ov": None,
             }
             if self._final is not None:
                 st["trans"] = torch.zeros((n, 6), dtype=torch.float64, device=dev)
@@ -201,6 +264,8 @@ class LitePosePipeline(object):
             # a captured graph bakes the plant hook's index tensors in: a different hook (or none) needs a new capture
             st["graph"] = None
             st["plant"] = plant
+            if st.get("ov") is not None:
+                st["ov"]["gF"] = [None, None]
         if st["trans"] is not None and st.get("trans_ver") != self._final_ver:
             if len(self._final[0]) != n:
                 raise ValueError("set_final_preds: %d centers for a batch of %d" % (len(self._final[0]), n))
@@ -282,12 +347,18 @@ class LitePosePipeline(object):
         main.wait_event(h2d)
         if sl["d2h_done"] is not None:
             main.wait_event(sl["d2h_done"])                  # the result slot is free again
-        packed = self.step_device(sl["x"], plant)
-        sl["out"].copy_(packed, non_blocking=True)
+        # network passes on this stream, parser of this step on the pipeline's parser stream (it overlaps the next
+        # step's network passes); the payload leaves through the result stream once the parser has finished
+        packed, parsed = self.step_device_overlapped(sl["x"], plant)
         sl["step_done"] = torch.cuda.Event()
-        sl["step_done"].record(main)
+        sl["step_done"].record(main)              # the input slot may be refilled after the network passes
         with torch.cuda.stream(a["res"]):
-            a["res"].wait_event(sl["step_done"])
+            a["res"].wait_event(parsed)
+            sl["out"].copy_(packed, non_blocking=True)
+            st_ = self._get_state(n, s_h, s_w, frames_pinned.dtype, plant)
+            done = torch.cuda.Event()
+            done.record(a["res"])
+            st_["ov"]["consumer_done"][st_["ov_last"]] = done
             if a["world"] > 1:
                 glist = list(sl["all"].unbind(0)) if a["rank"] == a["dst"] else None
                 dist.gather(sl["out"], glist, dst=a["dst"], group=group)
