@@ -74,6 +74,8 @@ class _EngineCache(object):
         import threading
         self.engines = {}
         self.lock = threading.RLock()
+        self.master_sig = None          # signature of the master module at the last DataParallel replication
+        self.keys = None                # its state_dict keys (replicas resolve their tensors by attribute path)
 
     def clear(self):
         with self.lock:
@@ -173,21 +175,41 @@ class LitePose(nn.Module):
             sig += t._version + (id(t) & 0xffff)
         return sig
 
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel replicates the master on every forward: publish the master's signature so that the replicas
+        # (whose tensors are fresh broadcasts without history) can tell a stale per-device engine from a current one
+        self._lp_cache.master_sig = self._lp_signature()
+        self._lp_cache.keys = list(self.state_dict().keys())
+        return super()._replicate_for_data_parallel()
+
+    def _lp_state(self):
+        """state_dict of this module; DataParallel replicas hold their (broadcast) tensors as plain attributes, not as
+        registered parameters, so their entries are resolved by attribute path from the master's key list."""
+        if not getattr(self, "_is_replica", False):
+            return self.state_dict()
+        out = {}
+        for k in self._lp_cache.keys:
+            obj = self
+            for part in k.split("."):
+                obj = getattr(obj, part)
+            out[k] = obj
+        return out
+
     def lp_engine(self, device=None):
         from litepose_b200.engine import LitePoseEngine
         dev = torch.device(device) if device is not None else next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("the litepose_b200 engine needs the module on a CUDA device")
         key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-        # DataParallel replicas receive freshly broadcast tensors on every forward (version 0, new identity): their
-        # engine is keyed by device only and lives until the master module invalidates the shared cache
+        # DataParallel replicas receive freshly broadcast tensors on every forward (version 0, new identity): they use
+        # the signature the master published when it was replicated
         replica = getattr(self, "_is_replica", False)
-        sig = None if replica else self._lp_signature()
+        sig = self._lp_cache.master_sig if replica else self._lp_signature()
         with self._lp_cache.lock:
             hit = self._lp_cache.engines.get(key)
-            if hit is not None and (replica or hit[1] is None or hit[1] == sig):
+            if hit is not None and hit[1] == sig:
                 return hit[0]
-            eng = LitePoseEngine(self.state_dict(), self.cfg_arch, torch.device("cuda", key[1]))
+            eng = LitePoseEngine(self._lp_state(), self.cfg_arch, torch.device("cuda", key[1]))
             self._lp_cache.engines[key] = (eng, sig)
             return eng
 

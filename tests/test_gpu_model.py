@@ -206,3 +206,28 @@ def test_pipeline_final_preds_on_device():
     pipe.set_final_preds(None)
     again = pipe.step(frames, plant)
     assert all(np.array_equal(x[0], y[0]) for x, y in zip(plain, again))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (nn.DataParallel over device_ids (0, 1))")
+def test_dataparallel_two_devices():
+    """reference valid.py:165 wraps the model in nn.DataParallel: replicas run on threads and share the drop-in module's
+    engine cache (one engine per device, lookups under a lock); outputs equal the single-device forward bit for bit."""
+    cfg = get_cfg(input_size=128)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, get_arch("XS")), 1).cuda(0).eval()
+    x = synth.make_frames(6, 128, seed=3).cuda(0)
+    with torch.no_grad():
+        single = model(x)
+        dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+        for _ in range(3):                      # replicas are re-created every call; engines are reused per device
+            multi = dp(x)
+    assert len(model._lp_cache.engines) == 2
+    for a, b in zip(single, multi):
+        assert b.device.index == 0 and torch.equal(a, b)
+    # invalidation reaches the replicas: an in-place weight update on the master changes both halves of the batch
+    with torch.no_grad():
+        model.first[0][0].weight.mul_(1.5)
+        again = dp(x)
+        ref = model(x)
+    for a, b, old in zip(ref, again, multi):
+        assert torch.equal(a, b) and not torch.equal(b, old)
