@@ -78,9 +78,11 @@ int lp_stem_conv3x3_s2(const void* x, int x_is_fp32, int flip_x, const void* w, 
  * y: NHWC fp16 [N,H/stride,W/stride,C].  C % 8 == 0; H, W even when stride == 2. */
 int lp_dwconv_f16(const void* x, const void* w, const float* bias, void* y, int N, int C, int H,
                   int W, int k, int stride, int act, lp_stream_t stream);
-/* Depthwise arithmetic: 0 = every product accumulated in fp32 (default; env LP_DW_PREC=1 changes
- * the default), 1 = the k taps of one kernel row accumulated in packed fp16 (HFMA2), row sums in
- * fp32.  Process-wide; set before building engines / capturing graphs. */
+/* Depthwise arithmetic of lp_dwconv_f16: 0 = every product accumulated in fp32 (FHFMA), 1 = the k taps of one kernel
+ * row accumulated in packed fp16 (HFMA2), row sums in fp32, 2 = fully packed fp16 (chains of two kernel rows folded
+ * into a running fp16 total - the arithmetic of the fused block kernels).  Any other value (or env LP_DW_PREC unset)
+ * selects the default: 2 for k = 7 and k = 3 (backbone, stem), 0 for k = 5 (heads).  Process-wide; set before
+ * building engines / capturing graphs. */
 void lp_set_dw_precision(int prec);
 int lp_get_dw_precision(void);
 

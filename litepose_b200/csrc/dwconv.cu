@@ -105,10 +105,15 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
         const int oy = by * BY, ox = bx * BX;           // tile-local output origin
         if (oy0 + oy >= Hout || ox0 + ox >= Wout) continue;   // micro-block fully outside
         float2 acc[BY][BX];
+        __half2 acch[BY][BX], part[BY][BX];      // PREC 2: running fp16 total + current two-row chain
+        const __half2 bh = __float22half2_rn(b2);
 #pragma unroll
         for (int i = 0; i < BY; ++i)
 #pragma unroll
-            for (int j = 0; j < BX; ++j) acc[i][j] = b2;
+            for (int j = 0; j < BX; ++j) {
+                acc[i][j] = b2;
+                acch[i][j] = bh;
+            }
 
         // slot c of a row holds input column (ox*S + c), or (ox*S + IC-1-c) when mirrored
         const __half2* base = tile_in + ((oy * S) * Cfg::IW + ox * S + (mir ? Cfg::IC - 1 : 0)) * (DW_CB / 2) + cp;
@@ -130,6 +135,21 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
                                 acc[i][j].x = fhfma(lo16(in[j * S + kx]), lo16(wv), acc[i][j].x);
                                 acc[i][j].y = fhfma(hi16(in[j * S + kx]), hi16(wv), acc[i][j].y);
                             }
+                        }
+                    } else if (PREC == 2) {
+                        // fully packed: chains of two kernel rows folded into a running fp16 total (dw_inner.cuh)
+#pragma unroll
+                        for (int kx = 0; kx < K; ++kx) {
+                            const __half2 wv = wreg[ky * K + kx];
+#pragma unroll
+                            for (int j = 0; j < BX; ++j) {
+                                if ((ky & 1) == 0 && kx == 0) part[i][j] = __hmul2(in[j * S + kx], wv);
+                                else part[i][j] = __hfma2(in[j * S + kx], wv, part[i][j]);
+                            }
+                        }
+                        if ((ky & 1) || ky == K - 1) {
+#pragma unroll
+                            for (int j = 0; j < BX; ++j) acch[i][j] = __hadd2(acch[i][j], part[i][j]);
                         }
                     } else {
 #pragma unroll
@@ -155,8 +175,15 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
                 for (int j = 0; j < BX; ++j) {
                     const int jj = mir ? BX - 1 - j : j;
                     if (full || (gy0 + i < Hout && gx0 + jj < Wout)) {
-                        const float vx = act_apply(acc[i][j].x, act), vy = act_apply(acc[i][j].y, act);
-                        *reinterpret_cast<__half2*>(ybase + ((size_t)i * Wout + jj) * C) = __floats2half2_rn(vx, vy);
+                        __half2 o;
+                        if (PREC == 2) {
+                            o = acch[i][j];
+                            if (act != LP_ACT_NONE) o = __hmax2(o, __floats2half2_rn(0.f, 0.f));
+                            if (act == LP_ACT_RELU6) o = __hmin2(o, __floats2half2_rn(6.f, 6.f));
+                        } else {
+                            o = __floats2half2_rn(act_apply(acc[i][j].x, act), act_apply(acc[i][j].y, act));
+                        }
+                        *reinterpret_cast<__half2*>(ybase + ((size_t)i * Wout + jj) * C) = o;
                     }
                 }
             }
@@ -164,12 +191,16 @@ dwconv_kernel(const __grid_constant__ CUtensorMap map_x, const __half* __restric
     }
 }
 
-static int g_dw_prec = -1;   // -1: read LP_DW_PREC once (default 0 = fp32 accumulation)
-static int dw_prec() {
-    if (g_dw_prec < 0) {
+// Depthwise arithmetic of this (unfused) kernel: 0 = fp32 accumulation (FHFMA), 1 = packed fp16 row sums added in fp32,
+// 2 = fully packed fp16 (grouped chains, like the fused block kernels).  Default (LP_DW_PREC unset): 2 for the
+// backbone / stem kernels k = 7 and k = 3, 0 for k = 5 (the SepConv heads feed the network outputs directly).
+static int g_dw_prec = -1;   // -1: read LP_DW_PREC once; -2: per-kernel-size default
+static int dw_prec(int k) {
+    if (g_dw_prec == -1) {
         const char* e = getenv("LP_DW_PREC");
-        g_dw_prec = (e && e[0] == '1') ? 1 : 0;
+        g_dw_prec = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -2;
     }
+    if (g_dw_prec == -2) return k == 5 ? 0 : 2;
     return g_dw_prec;
 }
 
@@ -201,8 +232,8 @@ static int launch_dw(const void* x, const void* w, const float* bias, void* y, i
 
 using namespace lp;
 
-extern "C" void lp_set_dw_precision(int prec) { lp::g_dw_prec = prec ? 1 : 0; }
-extern "C" int lp_get_dw_precision(void) { return lp::dw_prec(); }
+extern "C" void lp_set_dw_precision(int prec) { lp::g_dw_prec = (prec >= 0 && prec <= 2) ? prec : -2; }
+extern "C" int lp_get_dw_precision(void) { return lp::dw_prec(7); }
 
 extern "C" int lp_dwconv_f16(const void* x, const void* w, const float* bias, void* y, int N, int C, int H, int W, int k,
                              int stride, int act, lp_stream_t stream) {
@@ -218,11 +249,12 @@ extern "C" int lp_dwconv_f16(const void* x, const void* w, const float* bias, vo
         return LP_ERR_ALIGN;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    const int prec = dw_prec();
+    const int prec = dw_prec(k);
 #define LP_DW(KK, SS)                                                                      \
     if (k == KK && stride == SS)                                                           \
-        return prec ? launch_dw<KK, SS, 1>(x, w, bias, y, N, C, H, W, act, s)              \
-                    : launch_dw<KK, SS, 0>(x, w, bias, y, N, C, H, W, act, s);
+        return prec == 2 ? launch_dw<KK, SS, 2>(x, w, bias, y, N, C, H, W, act, s)         \
+             : prec == 1 ? launch_dw<KK, SS, 1>(x, w, bias, y, N, C, H, W, act, s)         \
+                         : launch_dw<KK, SS, 0>(x, w, bias, y, N, C, H, W, act, s);
     LP_DW(7, 1) LP_DW(7, 2) LP_DW(5, 1) LP_DW(5, 2) LP_DW(3, 1) LP_DW(3, 2)
 #undef LP_DW
     return LP_ERR_BAD_ARG;

@@ -43,7 +43,7 @@ def test_stem(fp32_in, flip, h, w):
     (7, 2, 144, 34 * 2, 18 * 2, 2), (5, 1, 24, 64, 64, 1), (5, 1, 40, 36, 68, 1), (3, 1, 32, 64, 64, 2),
     (3, 2, 16, 32, 32, 0), (7, 1, 8, 8, 8, 2),
 ])
-@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("prec", [0, 1, 2])
 def test_dwconv(k, s, c, h, w, act, prec):
     lib = _lib.load()
     lib.lp_set_dw_precision(prec)
@@ -60,7 +60,7 @@ def test_dwconv(k, s, c, h, w, act, prec):
     _lib.check(lib.lp_dwconv_f16(xd.data_ptr(), wd.data_ptr(), b.cuda().data_ptr(), y.data_ptr(), n, c, h, w, k, s,
                                  act, stream()), "dwconv")
     torch.cuda.synchronize()
-    lib.lp_set_dw_precision(0)
+    lib.lp_set_dw_precision(-1)           # back to the per-kernel-size default
     tol_check(from_nhwc(y), ref, what="dwconv k%d s%d c%d prec%d" % (k, s, c, prec))
 
 

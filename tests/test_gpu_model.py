@@ -155,7 +155,7 @@ def test_shipped_arch_golden_fp16_rowsum_depthwise(golden_dir, name, size):
         with torch.no_grad():
             o = model(x)
     finally:
-        lib.lp_set_dw_precision(0)
+        lib.lp_set_dw_precision(-1)
     _tol(o[0].cpu().numpy(), z["out0"], name + " prec1 out0")
     _tol(o[1].cpu().numpy(), z["out1"], name + " prec1 out1")
 
