@@ -278,6 +278,41 @@ def time_fused_kernel(n, ce, co, hw, device):
     return t, alg, flops
 
 
+def time_block_kernel(n, cin, ce, co, hw, device):
+    """The dominant kernel of the step: one stride-1 InvBottleneck (expand -> depthwise 7x7 -> project -> + identity) fused in
+    one launch, at the stage-0 shape of the workload."""
+    import numpy as np
+    import torch
+    from litepose_b200 import _lib
+    lib = _lib.load()
+    if not lib.lp_block_s1_supported(cin, ce, co):
+        return None
+    rs = np.random.RandomState(0)
+    x = torch.randn((n, hw, hw, cin), device=device).half()
+    we = np.ascontiguousarray((rs.randn(ce, cin) / cin ** 0.5).astype(np.float16)).view(np.uint16)
+    wek = np.zeros(lib.lp_block_s1_wexp_elems(cin, ce), np.uint16)
+    _lib.check(lib.lp_block_s1_pack_wexp(we.ctypes.data, cin, ce, wek.ctypes.data))
+    wed = torch.from_numpy(wek).view(torch.float16).to(device)
+    be, bd = torch.zeros(ce, device=device), torch.zeros(ce, device=device)
+    wd = (torch.randn((49, ce), device=device) * 0.1).half()
+    wp = np.ascontiguousarray((rs.randn(co, ce) / ce ** 0.5).astype(np.float16)).view(np.uint16)
+    wpk = np.zeros(lib.lp_pw1x1_packed_elems(ce, co), np.uint16)
+    bpk = np.zeros(lib.lp_pw1x1_packed_bias_elems(co), np.float32)
+    _lib.check(lib.lp_pw1x1_pack(wp.ctypes.data, None, ce, co, wpk.ctypes.data, bpk.ctypes.data))
+    wpd = torch.from_numpy(wpk).view(torch.float16).to(device)
+    bpd = torch.from_numpy(bpk).to(device)
+    out = torch.empty((n, hw, hw, co), dtype=torch.float16, device=device)
+    s = torch.cuda.current_stream().cuda_stream
+    t = _time_kernel(lambda: _lib.check(lib.lp_block_s1_f16(x.data_ptr(), wed.data_ptr(), be.data_ptr(), wd.data_ptr(),
+                                                            bd.data_ptr(), wpd.data_ptr(), bpd.data_ptr(), 1, out.data_ptr(), n,
+                                                            hw, hw, cin, ce, co, s)), device)
+    # algorithmic bytes: block input read once (+ once more as the identity), block output written, weights, biases
+    alg = 2 * (n * hw * hw * (2 * cin + co) + ce * cin + 49 * ce + ce * co) + 4 * (2 * ce + co)
+    macs_dw = 49 * n * hw * hw * ce
+    macs_tc = n * hw * hw * ce * (cin + co)
+    return t, alg, macs_dw, macs_tc
+
+
 def time_deconv_kernel(n, cr, cw, co, hw, device):
     """Fusion-deconv level (both ConvT branches + bias + ReLU) at the largest level of the workload."""
     import numpy as np
@@ -663,24 +698,54 @@ def main():
     c_stage0 = 6 * c0
     t_f, alg_f, flops_f = time_fused_kernel(B, c_stage0, c0, S // 4, dev)
     t_k, alg = time_dw7_kernel(B, c_stage0, S // 4, dev)
-    traffic = None
+    blk = time_block_kernel(B, c0, c_stage0, c0, S // 4, dev)
+    src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    # CUDA-core multiply-add ceiling of this part, measured by tools/microbench/fma_rates.cu (profiles/r2_fma_rates.jsonl):
+    # HFMA2 = 126 MAC/clk/SM (FFMA 93, FHFMA 108) -> x SMs x the clock sampled during the step
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_fma_rates.jsonl")) as f:
+            rates = [json.loads(l) for l in f if l.strip()]
+        hfma2_mac_clk_sm = max(r["macs_per_clk_per_sm"] for r in rates if "macs_per_clk_per_sm" in r)
+    except Exception:
+        hfma2_mac_clk_sm = 126.0
+    sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    fma_peak_tmacs = hfma2_mac_clk_sm * n_sm * sm_mhz * 1e6 / 1e12
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     except Exception:
         pass
-    src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    achieved = alg_f / t_f / 1e9
-    roofline = {"bound": "hbm", "kernel": "dw7_project_kernel (fused depthwise7x7+projection+identity) %dx%dx%dx%d->%d"
-                                          % (B, S // 4, S // 4, c_stage0, c0),
-                "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": traffic, "algorithmic_bytes": alg_f, "avg_launch_us": t_f * 1e6, "peak_source": src,
-                "note": "fusion removed the depthwise-output round trip (unfused algorithmic bytes: %d); the kernel is bound "
-                        "by the fp32 FMA pipe (49 MAC per expanded element, FHFMA), see fma_tflops" % (alg + alg_f),
-                "fma_tflops": flops_f / t_f / 1e12,
-                "unfused_dwconv_kernel": {"kernel": "dwconv_kernel<7,1> %dx%dx%dx%d" % (B, S // 4, S // 4, c_stage0),
-                                          "achieved": alg / t_k / 1e9, "frac": alg / t_k / 1e9 / peak_gbs,
-                                          "algorithmic_bytes": alg, "avg_launch_us": t_k * 1e6}}
+    fused_entry = {"kernel": "dw_project_kernel<7,0> (depthwise7x7+projection+identity on the HBM-resident expanded tensor) "
+                             "%dx%dx%dx%d->%d" % (B, S // 4, S // 4, c_stage0, c0),
+                   "achieved": alg_f / t_f / 1e9, "frac": alg_f / t_f / 1e9 / peak_gbs, "algorithmic_bytes": alg_f,
+                   "avg_launch_us": t_f * 1e6, "dw_tmacs": (flops_f / 2) / t_f / 1e12,
+                   "fma_frac": 49 * B * (S // 4) ** 2 * c_stage0 / t_f / 1e12 / fma_peak_tmacs}
+    if blk is not None:
+        t_b, alg_b, macs_dw, macs_tc = blk
+        achieved = alg_b / t_b / 1e9
+        roofline = {"bound": "hbm",
+                    "kernel": "block_s1_kernel (one stride-1 InvBottleneck: expand on tcgen05 -> depthwise7x7 -> projection "
+                              "-> identity, the 6x tensor stays on chip) %dx%dx%dx%d->%d->%d" % (B, S // 4, S // 4, c0, c_stage0, c0),
+                    "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                    "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_b,
+                    "avg_launch_us": t_b * 1e6, "peak_source": src,
+                    "limiter": "CUDA-core fp16 FMA pipe (49 MAC per expanded element; HBM carries only the narrow block "
+                               "input/output after block fusion, so the HBM fraction is low by construction)",
+                    "fma_pipe": {"achieved_tmacs": macs_dw / t_b / 1e12, "peak_tmacs": fma_peak_tmacs,
+                                 "frac": macs_dw / t_b / 1e12 / fma_peak_tmacs, "peak_mac_per_clk_per_sm": hfma2_mac_clk_sm,
+                                 "sm_mhz": sm_mhz, "peak_source": "profiles/r2_fma_rates.jsonl (HFMA2, measured on this pool)"},
+                    "tensor_tflops": 2 * macs_tc * 1.89 / t_b / 1e12,
+                    "unfused_dw_project_kernel": fused_entry,
+                    "unfused_dwconv_kernel": {"kernel": "dwconv_kernel<7,1> %dx%dx%dx%d" % (B, S // 4, S // 4, c_stage0),
+                                              "achieved": alg / t_k / 1e9, "frac": alg / t_k / 1e9 / peak_gbs,
+                                              "algorithmic_bytes": alg, "avg_launch_us": t_k * 1e6}}
+    else:
+        roofline = dict(fused_entry)
+        roofline.update({"bound": "hbm", "peak": peak_gbs, "unit": "GB/s", "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": src})
 
     ds = arch["deconv_setting"]
     cr_l2, cw_l2 = ds[-2], arch["backbone_setting"][0]["channel"]

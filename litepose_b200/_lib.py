@@ -35,6 +35,8 @@ SIGNATURES = {
     "lp_launch_count": (_c.c_uint64, []),
     "lp_reset_launch_count": (None, []),
     "lp_stem_conv3x3_s2": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lp_stem_fused_supported": (_i, [_i, _i, _i]),
+    "lp_stem_fused_f16": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "lp_dwconv_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lp_set_dw_precision": (None, [_i]),
     "lp_get_dw_precision": (_i, []),

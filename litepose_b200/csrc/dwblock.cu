@@ -245,28 +245,35 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         for (int i = 0; i < 16; ++i) be[i] = sBexp[s * BK_CB + hcol * 16 + i];
                         const __half2 zero2 = __floats2half2_rn(0.f, 0.f), six2 = __floats2half2_rn(6.f, 6.f);
 #pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) {
-                            uint32_t r[16];
-                            tc_ld16(taddr + mt * BK_CB, r);
+                        for (int mp = 0; mp < 2; ++mp) {
+                            // two M-tiles per round trip: both tcgen05.ld are in flight before the single wait
+                            uint32_t ra[16], rb[16];
+                            tc_ld16(taddr + (2 * mp) * BK_CB, ra);
+                            tc_ld16(taddr + (2 * mp + 1) * BK_CB, rb);
                             tc_wait_ld();
-                            const int pi = mt * 128 + q * 32 + lane;
-                            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
-                            if ((inside >> mt) & 1u) {
-                                // + bias in fp32, round to fp16, ReLU6 on the packed halves (clamping commutes with rounding)
-                                __half2* h0 = reinterpret_cast<__half2*>(&o0);
-                                __half2* h1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    h0[i] = __hmin2(__hmax2(__floats2half2_rn(__uint_as_float(r[2 * i]) + be[2 * i],
-                                                                              __uint_as_float(r[2 * i + 1]) + be[2 * i + 1]), zero2), six2);
-                                    h1[i] = __hmin2(__hmax2(__floats2half2_rn(__uint_as_float(r[8 + 2 * i]) + be[8 + 2 * i],
-                                                                              __uint_as_float(r[9 + 2 * i]) + be[9 + 2 * i]), zero2), six2);
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int mt = 2 * mp + hh;
+                                const uint32_t(&r)[16] = hh ? rb : ra;
+                                const int pi = mt * 128 + q * 32 + lane;
+                                uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
+                                if ((inside >> mt) & 1u) {
+                                    // + bias in fp32, round to fp16, ReLU6 on the packed halves (clamping commutes with rounding)
+                                    __half2* h0 = reinterpret_cast<__half2*>(&o0);
+                                    __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        h0[i] = __hmin2(__hmax2(__floats2half2_rn(__uint_as_float(r[2 * i]) + be[2 * i],
+                                                                                  __uint_as_float(r[2 * i + 1]) + be[2 * i + 1]), zero2), six2);
+                                        h1[i] = __hmin2(__hmax2(__floats2half2_rn(__uint_as_float(r[8 + 2 * i]) + be[8 + 2 * i],
+                                                                                  __uint_as_float(r[9 + 2 * i]) + be[9 + 2 * i]), zero2), six2);
+                                    }
                                 }
-                            }
-                            if (pi < BK_PIX) {
-                                // chunk-major slab: chunks 2*hcol, 2*hcol+1 of pixel pi (consecutive lanes -> consecutive 16 B)
-                                *reinterpret_cast<uint4*>(slab + (2 * hcol) * BK_CHUNK + pi * 16) = o0;
-                                *reinterpret_cast<uint4*>(slab + (2 * hcol + 1) * BK_CHUNK + pi * 16) = o1;
+                                if (pi < BK_PIX) {
+                                    // chunk-major slab: chunks 2*hcol, 2*hcol+1 of pixel pi (consecutive lanes -> consecutive 16 B)
+                                    *reinterpret_cast<uint4*>(slab + (2 * hcol) * BK_CHUNK + pi * 16) = o0;
+                                    *reinterpret_cast<uint4*>(slab + (2 * hcol + 1) * BK_CHUNK + pi * 16) = o1;
+                                }
                             }
                         }
                     }

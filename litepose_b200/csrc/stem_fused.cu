@@ -1,0 +1,377 @@
+// The whole stem in ONE kernel (reference lib/models/pose_mobilenet.py:36-41, lib/models/layers/layers.py:18-24):
+//   convbnrelu(3, 32, ker=3, stride=2) -> convbnrelu(32, 32, ker=3, stride=1, groups=32) -> Conv2d(32, C0, 1) + BN
+// reading the reference's NCHW image (fp32, or fp16 under network_to_half; optionally mirrored = the flip pass) and
+// writing the NHWC fp16 tensor x0 [N, H/2, W/2, C0] the backbone starts from.  Unfused, the two 32-channel
+// half-resolution intermediates (134 MB each at batch 32 / 512^2) are written and read back; here they stay on chip:
+// HBM traffic = the image once + x0 once.
+//
+// Per 14 x 6 output tile (persistent 128-thread CTAs, 5 per SM so that one CTA's barriers and MMA round trips hide
+// behind the others; the next tile's image patch is prefetched into registers):
+//   P0  haloed 3 x 17 x 36 image patch -> shared memory (fp16), 8/16-byte vector loads, zero outside the image
+//   P1  im2col of the 16 x 8 conv1 outputs the depthwise needs (27 taps, K padded to 32) -> 128B-swizzled K-major A1
+//   P2  tcgen05.mma  D1[128 px x 32] = A1 x W1^T            (one thread; fp32 accumulators in TMEM)
+//   P3  tcgen05.ld -> + bias -> ReLU6 -> fp16, ZERO outside the image (the depthwise pads conv1's OUTPUT with zeros)
+//       -> chunk-major tile [4 x 8ch][128 px][16 B] (conflict-free stores and loads, see dwblock.cu)
+//   P4  depthwise 3x3 on the CUDA cores: packed fp16 (HFMA2), + bias, ReLU6 -> 128B-swizzled K-major A2 (84 of 128 rows)
+//   P5  tcgen05.mma  D2[128 px x C0] = A2 x W3^T
+//   P6  tcgen05.ld -> + bias (no activation) -> fp16 -> 32/48-byte NHWC rows
+#include "common.cuh"
+
+namespace lp {
+
+// v2 geometry: the conv1 outputs a tile needs form exactly ONE 128-row M-tile (16 x 8), small CTAs (128 threads, ~38 KB
+// of shared memory) so that five are resident per SM and one CTA's barriers / MMA round trips hide behind the others;
+// the next tile's image patch is prefetched into registers while the current tile is processed.
+constexpr int SF_TW = 14, SF_TH = 6;                 // output tile (pixels of the H/2 x W/2 grid)
+constexpr int SF_CW = 16, SF_CH = 8;                 // conv1 outputs needed: (14+2) x (6+2) = 128
+constexpr int SF_OPIX = SF_TW * SF_TH;               // 84
+constexpr int SF_PH = 2 * SF_CH + 1;                 // image patch rows: 17
+constexpr int SF_PW = 36;                            // image patch columns (33 used, first = 2*ox0 - 4)
+constexpr int SF_PV = SF_PW / 4;                     // 4-pixel vectors per patch row
+constexpr int SF_NV = 3 * SF_PH * SF_PV;             // 459 vectors per patch
+constexpr int SF_THREADS = 128;
+constexpr int SF_PER = (SF_NV + SF_THREADS - 1) / SF_THREADS;   // 4 vectors per thread
+constexpr int SF_A = 128 * 128;                      // A1 (im2col) and, after conv1 has retired, A2 (depthwise output)
+constexpr int SF_B = 32 * 128;                       // weight tiles: up to 32 rows x 128 B
+constexpr int SF_TCHUNK = 2080;                      // chunk pitch of the conv1 tile: 128 * 16 + 32 (pitch = 32 mod 128)
+constexpr int SF_T = 4 * SF_TCHUNK;
+
+struct SfParams {
+    int N, H, W, Ho, Wo, C0, n_tile;
+    int tiles_x, tiles_y, num_tiles;
+    int flip_x, x_is_fp32;
+    const void* x;
+    const float* b1;        // [32]
+    const __half* w_dw;     // [9][32] tap-major
+    const float* b_dw;      // [32]
+    const float* b_pw;      // packed, n_tile
+    __half* out;            // [N, Ho, Wo, C0]
+};
+
+struct SfSmem {
+    alignas(1024) uint8_t a[SF_A];
+    alignas(1024) uint8_t b1[SF_B];
+    alignas(1024) uint8_t b2[SF_B];
+    alignas(16) uint8_t t[SF_T];
+    alignas(16) __half patch[3][SF_PH][SF_PW];
+    alignas(16) __half wdw[9][32];
+    float bias1[32], biasdw[32], biaspw[32];
+    uint64_t w_full, mma1, mma2;
+    uint32_t tmem_base;
+};
+
+// one 4-pixel vector of the image patch of tile t (zero outside the image), as two packed half2
+template <bool FP32>
+__device__ __forceinline__ uint2 sf_load_vec(const SfParams& p, int t, int i) {
+    const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
+    const int v = i % SF_PV, rr = i / SF_PV;
+    const int r = rr % SF_PH, c = rr / SF_PH;
+    const int gy = 2 * ty * SF_TH - 3 + r, gx = 2 * tx * SF_TW - 4 + 4 * v;
+    __half2 lo = __floats2half2_rn(0.f, 0.f), hi = lo;
+    if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {       // gx % 4 == 0 and W % 4 == 0: all four or none inside
+        const int sx = p.flip_x ? p.W - 4 - gx : gx;
+        const size_t off = (((size_t)n * 3 + c) * p.H + gy) * p.W + sx;
+        if (FP32) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + off));
+            if (p.flip_x) { lo = __floats2half2_rn(q.w, q.z); hi = __floats2half2_rn(q.y, q.x); }
+            else { lo = __floats2half2_rn(q.x, q.y); hi = __floats2half2_rn(q.z, q.w); }
+        } else {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.x) + off));
+            const __half2 a = *reinterpret_cast<const __half2*>(&q.x), b = *reinterpret_cast<const __half2*>(&q.y);
+            if (p.flip_x) { lo = __lowhigh2highlow(b); hi = __lowhigh2highlow(a); }
+            else { lo = a; hi = b; }
+        }
+    }
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return o;
+}
+
+template <bool FP32>
+__global__ void __launch_bounds__(SF_THREADS, 5)
+stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w3,
+                  const __grid_constant__ SfParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SfSmem& sm = *reinterpret_cast<SfSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_w1);
+        tma_prefetch_desc(&map_w3);
+        mbar_init(&sm.w_full, 1);
+        mbar_init(&sm.mma1, 1);
+        mbar_init(&sm.mma2, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tc_alloc(&sm.tmem_base, 64);
+        tc_relinquish();
+    }
+    for (int i = threadIdx.x; i < 9 * 32; i += SF_THREADS) sm.wdw[i / 32][i % 32] = p.w_dw[i];
+    if (threadIdx.x < 32) {
+        sm.bias1[threadIdx.x] = p.b1 ? p.b1[threadIdx.x] : 0.f;
+        sm.biasdw[threadIdx.x] = p.b_dw ? p.b_dw[threadIdx.x] : 0.f;
+        sm.biaspw[threadIdx.x] = (p.b_pw && threadIdx.x < p.n_tile) ? p.b_pw[threadIdx.x] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&sm.w_full, (uint32_t)(SF_B + p.n_tile * 128));
+        tma_load_2d(sm.b1, &map_w1, &sm.w_full, 0, 0);
+        tma_load_2d(sm.b2, &map_w3, &sm.w_full, 0, 0);
+    }
+    const uint32_t idesc1 = umma_idesc_f16(128, 32);
+    const uint32_t idesc2 = umma_idesc_f16(128, p.n_tile);
+    const __half2 zero2 = __floats2half2_rn(0.f, 0.f), six2 = __floats2half2_rn(6.f, 6.f);
+
+    // image patch of the first tile -> registers
+    uint2 pre[SF_PER];
+#pragma unroll
+    for (int u = 0; u < SF_PER; ++u) {
+        const int i = threadIdx.x + u * SF_THREADS;
+        pre[u] = make_uint2(0u, 0u);
+        if (i < SF_NV && (int)blockIdx.x < p.num_tiles) pre[u] = sf_load_vec<FP32>(p, blockIdx.x, i);
+    }
+
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx * SF_TW, oy0 = ty * SF_TH;
+
+        // ---- P0: prefetched patch registers -> shared memory; then start fetching the next tile's patch
+#pragma unroll
+        for (int u = 0; u < SF_PER; ++u) {
+            const int i = threadIdx.x + u * SF_THREADS;
+            if (i < SF_NV) {
+                const int v = i % SF_PV, rr = i / SF_PV;
+                *reinterpret_cast<uint2*>(&sm.patch[rr / SF_PH][rr % SF_PH][4 * v]) = pre[u];
+            }
+        }
+        __syncthreads();
+        {
+            const int tn = t + gridDim.x;
+#pragma unroll
+            for (int u = 0; u < SF_PER; ++u) {
+                const int i = threadIdx.x + u * SF_THREADS;
+                if (i < SF_NV && tn < p.num_tiles) pre[u] = sf_load_vec<FP32>(p, tn, i);
+            }
+        }
+
+        // ---- P1: im2col row of conv1 output r = y1l * 16 + x1l: k = c*9 + ky*3 + kx, K padded to 32
+        {
+            const int r = threadIdx.x;
+            const int y1l = r >> 4, x1l = r & 15;
+            __half v[32];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) v[c * 9 + ky * 3 + kx] = sm.patch[c][2 * y1l + ky][1 + 2 * x1l + kx];
+#pragma unroll
+            for (int k = 27; k < 32; ++k) v[k] = __float2half(0.f);
+            uint8_t* row = sm.a + r * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                __half* qh = reinterpret_cast<__half*>(&q);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) qh[e] = v[8 * j + e];
+                *reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4)) = q;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+
+        // ---- P2: conv1 on the tensor cores
+        if (threadIdx.x == 0) {
+            if (it == 0) mbar_wait(&sm.w_full, 0);
+            tc_fence_after();
+            for (int k = 0; k < 2; ++k)
+                tc_mma_f16(tmem_base, umma_desc_sw128(smem_u32(sm.a) + k * 32), umma_desc_sw128(smem_u32(sm.b1) + k * 32), idesc1,
+                           k > 0 ? 1u : 0u);
+            tc_commit(&sm.mma1);
+        }
+        mbar_wait(&sm.mma1, it & 1);
+        tc_fence_after();
+
+        // ---- P3: conv1 epilogue -> chunk-major fp16 tile (zero outside the image: the depthwise pads conv1's output)
+        {
+            const int r = warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            uint32_t ra[16], rb[16];
+            tc_ld16(taddr, ra);
+            tc_ld16(taddr + 16, rb);
+            tc_wait_ld();
+            const int y1 = oy0 - 1 + (r >> 4), x1 = ox0 - 1 + (r & 15);
+            const bool in = y1 >= 0 && y1 < p.Ho && x1 >= 0 && x1 < p.Wo;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (in) {
+                    __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 8 * j + 2 * e;
+                        const float a = __uint_as_float(c < 16 ? ra[c] : rb[c - 16]) + sm.bias1[c];
+                        const float b = __uint_as_float(c < 16 ? ra[c + 1] : rb[c - 15]) + sm.bias1[c + 1];
+                        h[e] = __hmin2(__hmax2(__floats2half2_rn(a, b), zero2), six2);
+                    }
+                }
+                *reinterpret_cast<uint4*>(sm.t + j * SF_TCHUNK + r * 16) = o;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- P4: depthwise 3x3 (+ bias, ReLU6) on the CUDA cores: thread = output pixel, 32 channels, packed fp16
+        if (threadIdx.x < SF_OPIX) {
+            const int pix = threadIdx.x;
+            const int py = pix / SF_TW, px = pix - py * SF_TW;
+            __half2 acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = __floats2half2_rn(sm.biasdw[2 * e], sm.biasdw[2 * e + 1]);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int rp = (py + ky) * SF_CW + px + kx;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(sm.t + j * SF_TCHUNK + rp * 16);
+                        const uint4 wq = *reinterpret_cast<const uint4*>(&sm.wdw[ky * 3 + kx][8 * j]);
+                        const __half2* xv = reinterpret_cast<const __half2*>(&q);
+                        const __half2* wv = reinterpret_cast<const __half2*>(&wq);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[4 * j + e] = __hfma2(xv[e], wv[e], acc[4 * j + e]);
+                    }
+                }
+            uint8_t* row = sm.a + pix * 128;          // A1 is dead (conv1 retired): its buffer now holds A2
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __hmin2(__hmax2(acc[4 * j + e], zero2), six2);
+                *reinterpret_cast<uint4*>(row + ((j ^ (pix & 7)) << 4)) = o;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+
+        // ---- P5: stem 1x1 on the tensor cores
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            for (int k = 0; k < 2; ++k)
+                tc_mma_f16(tmem_base + 32, umma_desc_sw128(smem_u32(sm.a) + k * 32), umma_desc_sw128(smem_u32(sm.b2) + k * 32),
+                           idesc2, k > 0 ? 1u : 0u);
+            tc_commit(&sm.mma2);
+        }
+        mbar_wait(&sm.mma2, it & 1);
+        tc_fence_after();
+
+        // ---- P6: output rows (no activation after the stem's 1x1 + BN)
+        {
+            const int pix = warp * 32 + lane;
+            const int py = pix / SF_TW, px = pix - py * SF_TW;
+            const int oy = oy0 + py, ox = ox0 + px;
+            const bool ok = pix < SF_OPIX && oy < p.Ho && ox < p.Wo;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + 32;
+            uint32_t r[16];
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                tc_ld16(taddr + c0, r);
+                tc_wait_ld();
+                if (ok && c0 < p.C0) {
+                    uint4 o0, o1;
+                    __half2* h0 = reinterpret_cast<__half2*>(&o0);
+                    __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        h0[e] = __floats2half2_rn(__uint_as_float(r[2 * e]) + sm.biaspw[c0 + 2 * e],
+                                                  __uint_as_float(r[2 * e + 1]) + sm.biaspw[c0 + 2 * e + 1]);
+                        h1[e] = __floats2half2_rn(__uint_as_float(r[8 + 2 * e]) + sm.biaspw[c0 + 8 + 2 * e],
+                                                  __uint_as_float(r[9 + 2 * e]) + sm.biaspw[c0 + 9 + 2 * e]);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(p.out + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.C0 + c0);
+                    op[0] = o0;
+                    if (c0 + 8 < p.C0) op[1] = o1;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();      // TMEM, the A buffer, the conv1 tile and the patch are free for the next tile
+        tc_fence_after();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, 64);
+    }
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+// 1 when lp_stem_fused_f16 handles this shape (else the caller runs lp_stem_conv3x3_s2 + lp_dwconv_f16 + lp_pw1x1_f16)
+extern "C" int lp_stem_fused_supported(int H, int W, int C0) {
+    return (H > 0 && W > 0 && H % 2 == 0 && W % 4 == 0 && C0 >= 8 && C0 % 8 == 0 && C0 <= 32) ? 1 : 0;
+}
+
+// w1_packed: [32][64] fp16, row co = the 27 BN-folded taps (k = c*9 + ky*3 + kx) of output channel co, zero padded.
+// w_dw: [9][32] tap-major BN-folded depthwise weights.  w_pw_packed / b_pw_packed: lp_pw1x1_pack(K = 32, N = C0).
+extern "C" int lp_stem_fused_f16(const void* x, int x_is_fp32, int flip_x, const void* w1_packed, const float* b1,
+                                 const void* w_dw, const float* b_dw, const void* w_pw_packed, const float* b_pw_packed,
+                                 void* out, int N, int H, int W, int C0, lp_stream_t stream) {
+    LP_CHECK_ARG(x && w1_packed && w_dw && w_pw_packed && out, "lp_stem_fused_f16: null pointer");
+    LP_CHECK_ARG(N > 0 && lp_stem_fused_supported(H, W, C0),
+                 "lp_stem_fused_f16: unsupported shape N=%d H=%d W=%d C0=%d (H even, W %% 4 == 0, C0 %% 8 == 0, C0 <= 32)", N,
+                 H, W, C0);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w1_packed) |
+         reinterpret_cast<uintptr_t>(w_pw_packed)) & 15) {
+        set_error("lp_stem_fused_f16: pointers must be 16-byte aligned");
+        return LP_ERR_ALIGN;
+    }
+    SfParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.H = H; p.W = W; p.Ho = H / 2; p.Wo = W / 2; p.C0 = C0;
+    p.n_tile = (C0 + 15) / 16 * 16;
+    p.tiles_x = (p.Wo + SF_TW - 1) / SF_TW;
+    p.tiles_y = (p.Ho + SF_TH - 1) / SF_TH;
+    p.num_tiles = p.tiles_x * p.tiles_y * N;
+    p.flip_x = flip_x; p.x_is_fp32 = x_is_fp32;
+    p.x = x; p.b1 = b1; p.w_dw = reinterpret_cast<const __half*>(w_dw); p.b_dw = b_dw; p.b_pw = b_pw_packed;
+    p.out = reinterpret_cast<__half*>(out);
+    CUtensorMap m1, m3;
+    {
+        uint64_t d[2] = {64u, 32u};
+        uint64_t s[1] = {128u};
+        uint32_t b[2] = {64u, 32u};
+        int rc = make_tmap(&m1, w1_packed, 2, d, s, b, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        uint64_t d3[2] = {64u, (uint64_t)p.n_tile};
+        uint32_t b3[2] = {64u, (uint32_t)p.n_tile};
+        rc = make_tmap(&m3, w_pw_packed, 2, d3, s, b3, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    const int smem = (int)sizeof(SfSmem);      // ~38 KB: five CTAs per SM
+    int grid = 5 * num_sms();
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    cudaError_t e;
+    if (x_is_fp32) {
+        e = cudaFuncSetAttribute((const void*)stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stem_fused)");
+        stem_fused_kernel<true><<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(m1, m3, p);
+    } else {
+        e = cudaFuncSetAttribute((const void*)stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stem_fused)");
+        stem_fused_kernel<false><<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(m1, m3, p);
+    }
+    LP_LAUNCH_CHECK("stem_fused_kernel");
+    return LP_OK;
+}

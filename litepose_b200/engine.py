@@ -59,6 +59,7 @@ class LitePoseEngine(object):
         self.fuse_dw_project = os.environ.get("LP_FUSE_DW_PROJECT", "1") != "0"
         self.fuse_heads = os.environ.get("LP_FUSE_HEADS", "1") != "0"
         self.fuse_block = os.environ.get("LP_FUSE_BLOCK", "1") != "0"
+        self.fuse_stem = os.environ.get("LP_FUSE_STEM", "1") != "0"
 
     # ------------------------------------------------------------------ folded checkpoint ("next" row 4)
     # BN fold (reference fuse_bn.py:81-162) and kernel packing become a load-time no-op: the file holds exactly the
@@ -160,8 +161,11 @@ class LitePoseEngine(object):
                              % (n_dec, tuple(sd["first.0.0.weight"].shape)))
         s, b = _fold(sd, "first.0.1")
         w = sd["first.0.0.weight"].float() * s.view(-1, 1, 1, 1)
+        w1p = torch.zeros((32, 64), dtype=torch.float16)
+        w1p[:, :27] = w.reshape(32, 27).half()
         P["stem"] = {"w": w.reshape(32, 27).half().contiguous().to(self.device),
-                     "b": b.contiguous().to(self.device)}
+                     "b": b.contiguous().to(self.device),
+                     "w1p": w1p.contiguous().to(self.device)}      # fused stem: [32][64] K-major rows (27 taps, zero padded)
         s, b = _fold(sd, "first.1.1")
         P["stem_dw"] = self._pack_dw(sd["first.1.0.weight"].float() * s.view(-1, 1, 1, 1), b)
         s, b = _fold(sd, "first.3")
@@ -250,20 +254,26 @@ class LitePoseEngine(object):
 
         plan = {"in_ptr": ctypes.c_void_p(0), "flip": ctypes.c_int(0)}
         h2, w2 = h // 2, w // 2
-        a0 = buf(n, h2, w2, 32)
-        a1 = buf(n, h2, w2, 32)
         x0 = buf(n, h2, w2, P["stem_pw"]["N"])
-        st = P["stem"]
-        ops.append(_Op("stem", lib.lp_stem_conv3x3_s2,
-                       [plan["in_ptr"], 1 if in_dtype == torch.float32 else 0, plan["flip"], st["w"].data_ptr(),
-                        st["b"].data_ptr(), a0.data_ptr(), n, h, w]))
-        d = P["stem_dw"]
-        ops.append(_Op("stem_dw", lib.lp_dwconv_f16, [a0.data_ptr(), d["w"].data_ptr(), d["b"].data_ptr(),
-                                                       a1.data_ptr(), n, 32, h2, w2, 3, 1, _lib.ACT_RELU6]))
-        q = P["stem_pw"]
-        ops.append(_Op("stem_pw", lib.lp_pw1x1_f16, [a1.data_ptr(), q["w"].data_ptr(), q["b"].data_ptr(), None,
-                                                      x0.data_ptr(), n * h2 * w2, q["K"], q["N"], _lib.ACT_NONE]))
-        keep = [a0, a1, x0]
+        st, d, q = P["stem"], P["stem_dw"], P["stem_pw"]
+        keep = [x0]
+        if self.fuse_stem and "w1p" in st and lib.lp_stem_fused_supported(h, w, q["N"]):
+            # conv3x3 s2 -> dw3x3 -> 1x1 in one kernel: the two 32-channel half-resolution tensors never reach HBM
+            ops.append(_Op("stem_fused", lib.lp_stem_fused_f16,
+                           [plan["in_ptr"], 1 if in_dtype == torch.float32 else 0, plan["flip"], st["w1p"].data_ptr(),
+                            st["b"].data_ptr(), d["w"].data_ptr(), d["b"].data_ptr(), q["w"].data_ptr(), q["b"].data_ptr(),
+                            x0.data_ptr(), n, h, w, q["N"]]))
+        else:
+            a0 = buf(n, h2, w2, 32)
+            a1 = buf(n, h2, w2, 32)
+            keep += [a0, a1]
+            ops.append(_Op("stem", lib.lp_stem_conv3x3_s2,
+                           [plan["in_ptr"], 1 if in_dtype == torch.float32 else 0, plan["flip"], st["w"].data_ptr(),
+                            st["b"].data_ptr(), a0.data_ptr(), n, h, w]))
+            ops.append(_Op("stem_dw", lib.lp_dwconv_f16, [a0.data_ptr(), d["w"].data_ptr(), d["b"].data_ptr(),
+                                                           a1.data_ptr(), n, 32, h2, w2, 3, 1, _lib.ACT_RELU6]))
+            ops.append(_Op("stem_pw", lib.lp_pw1x1_f16, [a1.data_ptr(), q["w"].data_ptr(), q["b"].data_ptr(), None,
+                                                          x0.data_ptr(), n * h2 * w2, q["K"], q["N"], _lib.ACT_NONE]))
         x_list = [(x0, h2, w2)]
         cur, ch, cw_ = x0, h2, w2
         # scratch for the expanded tensors, sized for the largest block

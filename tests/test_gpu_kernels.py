@@ -288,3 +288,41 @@ def test_block_s1_unsupported_shapes():
     rc = lib.lp_block_s1_f16(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), None, x.data_ptr(), None, 0, x.data_ptr(),
                              1, 16, 16, 120, 720, 120, stream())
     assert rc != 0 and b"unsupported shape" in lib.lp_last_error()
+
+
+@pytest.mark.parametrize("n,h,w,c0,fp32_in,flip", [
+    (2, 64, 64, 16, True, False), (1, 128, 96, 16, False, True), (2, 48, 80, 24, False, False),
+    (1, 32, 36, 16, True, True),                 # ragged tiles (Wo = 18, Ho = 16)
+    (3, 256, 256, 16, False, False),             # many tiles per persistent CTA
+    (1, 512, 512, 16, False, True),
+])
+def test_stem_fused(n, h, w, c0, fp32_in, flip):
+    """conv3x3 s2 + BN + ReLU6 -> dw3x3 + BN + ReLU6 -> 1x1 + BN in one kernel vs the fp32 reference with fp16 storage of
+    the two intermediates (what the three unfused kernels compute); reference lib/models/pose_mobilenet.py:36-41"""
+    lib = _lib.load()
+    assert lib.lp_stem_fused_supported(h, w, c0) == 1
+    g = torch.Generator().manual_seed(h + w + c0)
+    xin = q16(torch.randn(n, 3, h, w, generator=g))
+    w1 = q16(torch.randn(32, 3, 3, 3, generator=g) * 0.3)
+    b1 = torch.randn(32, generator=g) * 0.2
+    wd = q16(torch.randn(32, 1, 3, 3, generator=g) * 0.3)
+    bd = torch.randn(32, generator=g) * 0.2
+    w3 = q16(torch.randn(c0, 32, generator=g) / 32 ** 0.5)
+    b3 = torch.randn(c0, generator=g) * 0.1
+    src = torch.flip(xin, [3]) if flip else xin
+    a0 = q16(F.relu6(F.conv2d(src, w1, b1, 2, 1)))
+    a1 = q16(F.relu6(F.conv2d(a0, wd, bd, 1, 1, 1, 32)))
+    ref = F.conv2d(a1, w3.view(c0, 32, 1, 1), b3)
+    w1p = torch.zeros(32, 64, dtype=torch.float16)
+    w1p[:, :27] = w1.reshape(32, 27).half()
+    w3k, b3k = pack_pw(w3, b3)
+    xd = (xin if fp32_in else xin.half()).cuda().contiguous()
+    w1d, b1d = w1p.cuda(), b1.cuda()
+    wdd, bdd = wd.reshape(32, 9).t().contiguous().half().cuda(), bd.cuda()
+    y = torch.full((n, h // 2, w // 2, c0), float("nan"), dtype=torch.float16, device="cuda")
+    for _ in range(2):
+        _lib.check(lib.lp_stem_fused_f16(xd.data_ptr(), 1 if fp32_in else 0, 1 if flip else 0, w1d.data_ptr(), b1d.data_ptr(),
+                                         wdd.data_ptr(), bdd.data_ptr(), w3k.data_ptr(), b3k.data_ptr(), y.data_ptr(), n, h, w,
+                                         c0, stream()), "stem_fused")
+    torch.cuda.synchronize()
+    tol_check(from_nhwc(y), ref, what="stem_fused c0=%d %dx%d" % (c0, h, w))
