@@ -5,35 +5,39 @@
 // half-resolution intermediates (134 MB each at batch 32 / 512^2) are written and read back; here they stay on chip:
 // HBM traffic = the image once + x0 once.
 //
-// Per 14 x 6 output tile (persistent 128-thread CTAs, 5 per SM so that one CTA's barriers and MMA round trips hide
+// Per 16 x 8 output tile (persistent 128-thread CTAs, 3 per SM so that one CTA's barriers and MMA round trips hide
 // behind the others; the next tile's image patch is prefetched into registers):
-//   P0  haloed 3 x 17 x 36 image patch -> shared memory (fp16), 8/16-byte vector loads, zero outside the image
-//   P1  im2col of the 16 x 8 conv1 outputs the depthwise needs (27 taps, K padded to 32) -> 128B-swizzled K-major A1
-//   P2  tcgen05.mma  D1[128 px x 32] = A1 x W1^T            (one thread; fp32 accumulators in TMEM)
+//   P0  haloed 3 x 21 x 40 image patch -> shared memory (fp16), 8/16-byte vector loads, zero outside the image
+//   P1  im2col of the 18 x 10 conv1 outputs the depthwise needs (27 taps, K padded to 32) -> 128B-swizzled K-major A1
+//   P2  tcgen05.mma  D1[256 px x 32] = A1 x W1^T            (one thread; fp32 accumulators in TMEM)
 //   P3  tcgen05.ld -> + bias -> ReLU6 -> fp16, ZERO outside the image (the depthwise pads conv1's OUTPUT with zeros)
-//       -> chunk-major tile [4 x 8ch][128 px][16 B] (conflict-free stores and loads, see dwblock.cu)
-//   P4  depthwise 3x3 on the CUDA cores: packed fp16 (HFMA2), + bias, ReLU6 -> 128B-swizzled K-major A2 (84 of 128 rows)
+//       -> chunk-major tile [4 x 8ch][180 px][16 B] (conflict-free stores and loads, see dwblock.cu)
+//   P4  depthwise 3x3 on the CUDA cores (register-blocked HFMA2 loop of dw_inner.cuh), + bias, ReLU6
+//       -> 128B-swizzled K-major A2 [128 px x 32]
 //   P5  tcgen05.mma  D2[128 px x C0] = A2 x W3^T
 //   P6  tcgen05.ld -> + bias (no activation) -> fp16 -> 32/48-byte NHWC rows
 #include "common.cuh"
+#include "dw_inner.cuh"
 
 namespace lp {
 
-// v2 geometry: the conv1 outputs a tile needs form exactly ONE 128-row M-tile (16 x 8), small CTAs (128 threads, ~38 KB
-// of shared memory) so that five are resident per SM and one CTA's barriers / MMA round trips hide behind the others;
-// the next tile's image patch is prefetched into registers while the current tile is processed.
-constexpr int SF_TW = 14, SF_TH = 6;                 // output tile (pixels of the H/2 x W/2 grid)
-constexpr int SF_CW = 16, SF_CH = 8;                 // conv1 outputs needed: (14+2) x (6+2) = 128
-constexpr int SF_OPIX = SF_TW * SF_TH;               // 84
-constexpr int SF_PH = 2 * SF_CH + 1;                 // image patch rows: 17
-constexpr int SF_PW = 36;                            // image patch columns (33 used, first = 2*ox0 - 4)
+// Geometry: 16 x 8 output tile = 8 micro-blocks of 4 x 4 pixels x 16 channel pairs = 128 threads for the depthwise (the
+// register-blocked loop of dw_inner.cuh: 36 LDS.32 per 16 outputs instead of 36 LDS.128 per output - the first version
+// of this kernel, one thread per output pixel, was bound by the shared-memory pipe at 72 %); the 18 x 10 conv1 outputs
+// it needs are two 128-row M-tiles.  Small CTAs (128 threads, ~58 KB) so that three are resident per SM and one CTA's
+// barriers / MMA round trips hide behind the others; the next tile's image patch is prefetched into registers.
+constexpr int SF_TW = 16, SF_TH = 8;                 // output tile (pixels of the H/2 x W/2 grid)
+constexpr int SF_CW = SF_TW + 2, SF_CH = SF_TH + 2;  // conv1 outputs needed: 18 x 10
+constexpr int SF_CPIX = SF_CW * SF_CH;               // 180
+constexpr int SF_PH = 2 * SF_CH + 1;                 // image patch rows: 21
+constexpr int SF_PW = 40;                            // image patch columns (37 used, first = 2*ox0 - 4)
 constexpr int SF_PV = SF_PW / 4;                     // 4-pixel vectors per patch row
-constexpr int SF_NV = 3 * SF_PH * SF_PV;             // 459 vectors per patch
+constexpr int SF_NV = 3 * SF_PH * SF_PV;             // 630 vectors per patch
 constexpr int SF_THREADS = 128;
-constexpr int SF_PER = (SF_NV + SF_THREADS - 1) / SF_THREADS;   // 4 vectors per thread
-constexpr int SF_A = 128 * 128;                      // A1 (im2col) and, after conv1 has retired, A2 (depthwise output)
+constexpr int SF_PER = (SF_NV + SF_THREADS - 1) / SF_THREADS;   // 5 vectors per thread
+constexpr int SF_A = 2 * 128 * 128;                  // A1 (im2col, two M-tiles); its first half holds A2 once conv1 has retired
 constexpr int SF_B = 32 * 128;                       // weight tiles: up to 32 rows x 128 B
-constexpr int SF_TCHUNK = 2080;                      // chunk pitch of the conv1 tile: 128 * 16 + 32 (pitch = 32 mod 128)
+constexpr int SF_TCHUNK = 2976;                      // chunk pitch of the conv1 tile: 180 * 16 + 96 (pitch = 32 mod 128)
 constexpr int SF_T = 4 * SF_TCHUNK;
 
 struct SfParams {
@@ -60,27 +64,42 @@ struct SfSmem {
     uint32_t tmem_base;
 };
 
-// one 4-pixel vector of the image patch of tile t (zero outside the image), as two packed half2
+// one 4-pixel vector of the image patch of tile t, RAW (zero outside the image): the load must not be consumed before
+// the patch is written to shared memory one tile later, or the prefetch stalls on the spot (the first version applied
+// the mirror permutation here and spent 26 % of its stall samples on it)
 template <bool FP32>
-__device__ __forceinline__ uint2 sf_load_vec(const SfParams& p, int t, int i) {
+__device__ __forceinline__ uint4 sf_load_vec(const SfParams& p, int t, int i) {
     const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
     const int v = i % SF_PV, rr = i / SF_PV;
     const int r = rr % SF_PH, c = rr / SF_PH;
     const int gy = 2 * ty * SF_TH - 3 + r, gx = 2 * tx * SF_TW - 4 + 4 * v;
-    __half2 lo = __floats2half2_rn(0.f, 0.f), hi = lo;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {       // gx % 4 == 0 and W % 4 == 0: all four or none inside
         const int sx = p.flip_x ? p.W - 4 - gx : gx;
         const size_t off = (((size_t)n * 3 + c) * p.H + gy) * p.W + sx;
         if (FP32) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + off));
-            if (p.flip_x) { lo = __floats2half2_rn(q.w, q.z); hi = __floats2half2_rn(q.y, q.x); }
-            else { lo = __floats2half2_rn(q.x, q.y); hi = __floats2half2_rn(q.z, q.w); }
+            o = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.x) + off));
         } else {
             const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.x) + off));
-            const __half2 a = *reinterpret_cast<const __half2*>(&q.x), b = *reinterpret_cast<const __half2*>(&q.y);
-            if (p.flip_x) { lo = __lowhigh2highlow(b); hi = __lowhigh2highlow(a); }
-            else { lo = a; hi = b; }
+            o.x = q.x;
+            o.y = q.y;
         }
+    }
+    return o;
+}
+// raw vector -> four fp16 pixels in patch order (mirrored for the flip pass)
+template <bool FP32>
+__device__ __forceinline__ uint2 sf_pack_vec(uint4 raw, int flip_x) {
+    __half2 lo, hi;
+    if (FP32) {
+        const float f0 = __uint_as_float(raw.x), f1 = __uint_as_float(raw.y), f2 = __uint_as_float(raw.z),
+                    f3 = __uint_as_float(raw.w);
+        if (flip_x) { lo = __floats2half2_rn(f3, f2); hi = __floats2half2_rn(f1, f0); }
+        else { lo = __floats2half2_rn(f0, f1); hi = __floats2half2_rn(f2, f3); }
+    } else {
+        const __half2 a = *reinterpret_cast<const __half2*>(&raw.x), b = *reinterpret_cast<const __half2*>(&raw.y);
+        if (flip_x) { lo = __lowhigh2highlow(b); hi = __lowhigh2highlow(a); }
+        else { lo = a; hi = b; }
     }
     uint2 o;
     o.x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -89,7 +108,7 @@ __device__ __forceinline__ uint2 sf_load_vec(const SfParams& p, int t, int i) {
 }
 
 template <bool FP32>
-__global__ void __launch_bounds__(SF_THREADS, 5)
+__global__ void __launch_bounds__(SF_THREADS, 3)
 stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w3,
                   const __grid_constant__ SfParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -105,7 +124,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
         fence_barrier_init();
     }
     if (warp == 1) {
-        tc_alloc(&sm.tmem_base, 64);
+        tc_alloc(&sm.tmem_base, 128);
         tc_relinquish();
     }
     for (int i = threadIdx.x; i < 9 * 32; i += SF_THREADS) sm.wdw[i / 32][i % 32] = p.w_dw[i];
@@ -128,11 +147,11 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
     const __half2 zero2 = __floats2half2_rn(0.f, 0.f), six2 = __floats2half2_rn(6.f, 6.f);
 
     // image patch of the first tile -> registers
-    uint2 pre[SF_PER];
+    uint4 pre[SF_PER];
 #pragma unroll
     for (int u = 0; u < SF_PER; ++u) {
         const int i = threadIdx.x + u * SF_THREADS;
-        pre[u] = make_uint2(0u, 0u);
+        pre[u] = make_uint4(0u, 0u, 0u, 0u);
         if (i < SF_NV && (int)blockIdx.x < p.num_tiles) pre[u] = sf_load_vec<FP32>(p, blockIdx.x, i);
     }
 
@@ -147,7 +166,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
             const int i = threadIdx.x + u * SF_THREADS;
             if (i < SF_NV) {
                 const int v = i % SF_PV, rr = i / SF_PV;
-                *reinterpret_cast<uint2*>(&sm.patch[rr / SF_PH][rr % SF_PH][4 * v]) = pre[u];
+                *reinterpret_cast<uint2*>(&sm.patch[rr / SF_PH][rr % SF_PH][4 * v]) = sf_pack_vec<FP32>(pre[u], p.flip_x);
             }
         }
         __syncthreads();
@@ -160,10 +179,10 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
             }
         }
 
-        // ---- P1: im2col row of conv1 output r = y1l * 16 + x1l: k = c*9 + ky*3 + kx, K padded to 32
-        {
-            const int r = threadIdx.x;
-            const int y1l = r >> 4, x1l = r & 15;
+        // ---- P1: im2col rows of the 18 x 10 conv1 outputs (row r = y1l * 18 + x1l): k = c*9 + ky*3 + kx, K padded to 32
+#pragma unroll 1
+        for (int r = threadIdx.x; r < SF_CPIX; r += SF_THREADS) {
+            const int y1l = r / SF_CW, x1l = r - y1l * SF_CW;
             __half v[32];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -173,7 +192,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
                     for (int kx = 0; kx < 3; ++kx) v[c * 9 + ky * 3 + kx] = sm.patch[c][2 * y1l + ky][1 + 2 * x1l + kx];
 #pragma unroll
             for (int k = 27; k < 32; ++k) v[k] = __float2half(0.f);
-            uint8_t* row = sm.a + r * 128;
+            uint8_t* row = sm.a + (r >> 7) * 16384 + (r & 127) * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 q;
@@ -190,74 +209,60 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
         if (threadIdx.x == 0) {
             if (it == 0) mbar_wait(&sm.w_full, 0);
             tc_fence_after();
-            for (int k = 0; k < 2; ++k)
-                tc_mma_f16(tmem_base, umma_desc_sw128(smem_u32(sm.a) + k * 32), umma_desc_sw128(smem_u32(sm.b1) + k * 32), idesc1,
-                           k > 0 ? 1u : 0u);
+            for (int mt = 0; mt < 2; ++mt)
+                for (int k = 0; k < 2; ++k)
+                    tc_mma_f16(tmem_base + mt * 32, umma_desc_sw128(smem_u32(sm.a) + mt * 16384 + k * 32),
+                               umma_desc_sw128(smem_u32(sm.b1) + k * 32), idesc1, k > 0 ? 1u : 0u);
             tc_commit(&sm.mma1);
         }
         mbar_wait(&sm.mma1, it & 1);
         tc_fence_after();
 
         // ---- P3: conv1 epilogue -> chunk-major fp16 tile (zero outside the image: the depthwise pads conv1's output)
-        {
-            const int r = warp * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r = mt * 128 + warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + mt * 32;
             uint32_t ra[16], rb[16];
             tc_ld16(taddr, ra);
             tc_ld16(taddr + 16, rb);
             tc_wait_ld();
-            const int y1 = oy0 - 1 + (r >> 4), x1 = ox0 - 1 + (r & 15);
-            const bool in = y1 >= 0 && y1 < p.Ho && x1 >= 0 && x1 < p.Wo;
+            if (r < SF_CPIX) {
+                const int y1l = r / SF_CW, x1l = r - y1l * SF_CW;
+                const int y1 = oy0 - 1 + y1l, x1 = ox0 - 1 + x1l;
+                const bool in = y1 >= 0 && y1 < p.Ho && x1 >= 0 && x1 < p.Wo;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (in) {
-                    __half2* h = reinterpret_cast<__half2*>(&o);
+                for (int j = 0; j < 4; ++j) {
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (in) {
+                        __half2* h = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = 8 * j + 2 * e;
-                        const float a = __uint_as_float(c < 16 ? ra[c] : rb[c - 16]) + sm.bias1[c];
-                        const float b = __uint_as_float(c < 16 ? ra[c + 1] : rb[c - 15]) + sm.bias1[c + 1];
-                        h[e] = __hmin2(__hmax2(__floats2half2_rn(a, b), zero2), six2);
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = 8 * j + 2 * e;
+                            const float a = __uint_as_float(c < 16 ? ra[c] : rb[c - 16]) + sm.bias1[c];
+                            const float b = __uint_as_float(c < 16 ? ra[c + 1] : rb[c - 15]) + sm.bias1[c + 1];
+                            h[e] = __hmin2(__hmax2(__floats2half2_rn(a, b), zero2), six2);
+                        }
                     }
+                    *reinterpret_cast<uint4*>(sm.t + j * SF_TCHUNK + r * 16) = o;
                 }
-                *reinterpret_cast<uint4*>(sm.t + j * SF_TCHUNK + r * 16) = o;
             }
         }
         tc_fence_before();
         __syncthreads();
 
-        // ---- P4: depthwise 3x3 (+ bias, ReLU6) on the CUDA cores: thread = output pixel, 32 channels, packed fp16
-        if (threadIdx.x < SF_OPIX) {
-            const int pix = threadIdx.x;
-            const int py = pix / SF_TW, px = pix - py * SF_TW;
-            __half2 acc[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) acc[e] = __floats2half2_rn(sm.biasdw[2 * e], sm.biasdw[2 * e + 1]);
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int rp = (py + ky) * SF_CW + px + kx;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 q = *reinterpret_cast<const uint4*>(sm.t + j * SF_TCHUNK + rp * 16);
-                        const uint4 wq = *reinterpret_cast<const uint4*>(&sm.wdw[ky * 3 + kx][8 * j]);
-                        const __half2* xv = reinterpret_cast<const __half2*>(&q);
-                        const __half2* wv = reinterpret_cast<const __half2*>(&wq);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[4 * j + e] = __hfma2(xv[e], wv[e], acc[4 * j + e]);
-                    }
-                }
-            uint8_t* row = sm.a + pix * 128;          // A1 is dead (conv1 retired): its buffer now holds A2
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                __half2* h = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __hmin2(__hmax2(acc[4 * j + e], zero2), six2);
-                *reinterpret_cast<uint4*>(row + ((j ^ (pix & 7)) << 4)) = o;
-            }
+        // ---- P4: depthwise 3x3 (+ bias, ReLU6) on the CUDA cores: thread = channel pair x 4x4 micro-block, packed fp16
+        {
+            const int cp = threadIdx.x & 15, sub = (threadIdx.x >> 4) & 1;
+            const bool mir = sub != 0;
+            const int blk = (warp << 1) | sub;              // 8 micro-blocks: 2 rows x 4 columns of 4x4 pixels
+            const int oy = (blk >> 2) * 4, ox = (blk & 3) * 4;
+            const __half2 bh = __floats2half2_rn(sm.biasdw[2 * cp], sm.biasdw[2 * cp + 1]);
+            const __half2* tile_in = reinterpret_cast<const __half2*>(sm.t + (cp >> 2) * SF_TCHUNK) + (cp & 3);
+            __half2 acc[4][4];
+            dw_slab_hfma2<3, 4, SF_CW, 32, 4>(tile_in, reinterpret_cast<const __half2*>(&sm.wdw[0][0]), cp, mir, oy, ox, bh, acc);
+            // A1 is dead (conv1 retired): the first M-tile of its buffer now holds A2 (128 pixels x 32 channels)
+            dw_store_a<4>(sm.a, 16384, acc, oy, ox, mir, cp >> 2, cp);
         }
         fence_proxy_async();
         __syncthreads();
@@ -266,7 +271,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
         if (threadIdx.x == 0) {
             tc_fence_after();
             for (int k = 0; k < 2; ++k)
-                tc_mma_f16(tmem_base + 32, umma_desc_sw128(smem_u32(sm.a) + k * 32), umma_desc_sw128(smem_u32(sm.b2) + k * 32),
+                tc_mma_f16(tmem_base + 64, umma_desc_sw128(smem_u32(sm.a) + k * 32), umma_desc_sw128(smem_u32(sm.b2) + k * 32),
                            idesc2, k > 0 ? 1u : 0u);
             tc_commit(&sm.mma2);
         }
@@ -276,10 +281,9 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
         // ---- P6: output rows (no activation after the stem's 1x1 + BN)
         {
             const int pix = warp * 32 + lane;
-            const int py = pix / SF_TW, px = pix - py * SF_TW;
-            const int oy = oy0 + py, ox = ox0 + px;
-            const bool ok = pix < SF_OPIX && oy < p.Ho && ox < p.Wo;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + 32;
+            const int oy = oy0 + (pix >> 4), ox = ox0 + (pix & 15);
+            const bool ok = oy < p.Ho && ox < p.Wo;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + 64;
             uint32_t r[16];
             for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
                 tc_ld16(taddr + c0, r);
@@ -310,7 +314,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tc_dealloc(tmem_base, 64);
+        tc_dealloc(tmem_base, 128);
     }
 }
 
@@ -359,8 +363,8 @@ extern "C" int lp_stem_fused_f16(const void* x, int x_is_fp32, int flip_x, const
         rc = make_tmap(&m3, w_pw_packed, 2, d3, s, b3, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    const int smem = (int)sizeof(SfSmem);      // ~38 KB: five CTAs per SM
-    int grid = 5 * num_sms();
+    const int smem = (int)sizeof(SfSmem);      // ~58 KB: three CTAs per SM
+    int grid = 3 * num_sms();
     if (grid > p.num_tiles) grid = p.num_tiles;
     cudaError_t e;
     if (x_is_fp32) {
