@@ -41,7 +41,7 @@ struct FpBars {
     uint64_t in_full[FP_NIN], in_empty[FP_NIN];
     uint64_t a_full, a_empty;
     uint64_t b_full[FP_NB], b_empty[FP_NB];
-    uint64_t tmem_full, tmem_empty;
+    uint64_t tmem_full[2], tmem_empty[2];   // heads: two accumulator buffers (deferred epilogue); blocks use [0]
     uint32_t tmem_base, pad;
 };
 
@@ -94,8 +94,7 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         mbar_init(&bars->a_full, FP_DW_WARPS);
         mbar_init(&bars->a_empty, 1);
         for (int i = 0; i < FP_NB; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
-        mbar_init(&bars->tmem_full, 1);
-        mbar_init(&bars->tmem_empty, FP_DW_WARPS);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], FP_DW_WARPS); }
         fence_barrier_init();
     }
     if (warp == FP_DW_WARPS + 1) {
@@ -144,7 +143,10 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             uint32_t bs = 0, bph = 0, kbc = 0;
             int it = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-                mbar_wait_backoff(&bars->tmem_empty, (it & 1) ^ 1);
+                // heads alternate between two accumulator buffers so that the depthwise warps can run the next tile while
+                // this tile's MMAs retire (the epilogue of tile i follows the depthwise of tile i+1)
+                const int ab = HEAD ? (it & 1) : 0;
+                mbar_wait_backoff(&bars->tmem_empty[ab], (HEAD ? ((it >> 1) & 1) : (it & 1)) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
                     mbar_wait_backoff(&bars->a_full, kbc & 1);
@@ -155,14 +157,14 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     for (int mt = 0; mt < 2; ++mt) {
                         const uint32_t a_base = smem_u32(sA + mt * FP_A_TILE);
                         for (int k = 0; k < k16; ++k)
-                            tc_mma_f16(tmem_base + mt * p.n_tile, umma_desc_sw128(a_base + k * 32),
+                            tc_mma_f16(tmem_base + ab * 2 * p.n_tile + mt * p.n_tile, umma_desc_sw128(a_base + k * 32),
                                        umma_desc_sw128(b_base + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&bars->a_empty);
                     tc_commit(&bars->b_empty[bs]);
                     if (++bs == FP_NB) { bs = 0; bph ^= 1; }
                 }
-                tc_commit(&bars->tmem_full);
+                tc_commit(&bars->tmem_full[ab]);
             }
         }
     } else {
@@ -177,6 +179,86 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int oy = by * 4, ox = bx * 4;
         const int cstep = mir ? -(FP_CB / 2) : (FP_CB / 2);
         uint32_t iu = 0, kbc = 0;                          // slabs consumed by this group, K blocks finished
+        // ---- epilogue of tile te (iteration ite): accumulator row = pixel (mt = warp>>2, row = (warp&3)*32 + lane)
+        auto epilogue = [&](int te, int ite) {
+            const int tx = te % p.tiles_x, ty = (te / p.tiles_x) % p.tiles_y, n = te / (p.tiles_x * p.tiles_y);
+            const int ab = HEAD ? (ite & 1) : 0;
+            mbar_wait(&bars->tmem_full[ab], HEAD ? ((ite >> 1) & 1) : (ite & 1));
+            tc_fence_after();
+        {
+            const int mt = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+            const int chalf = warp >> 3;               // the two groups take alternate 16-column chunks
+            const int py = mt * 8 + (row >> 4), px = row & 15;
+            const int gy = ty * FP_T + py, gx = tx * FP_T + px;
+            const bool valid = gy < p.H && gx < p.W;
+            const size_t off = (((size_t)n * p.H + gy) * p.W + gx) * p.Co;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ab * 2 * p.n_tile + mt * p.n_tile;
+            uint32_t r[16];
+            for (int c0 = chalf * 16; c0 < p.n_tile; c0 += 32) {
+                tc_ld16(taddr + c0, r);
+                tc_wait_ld();
+                if (HEAD) {
+                    if (valid) {
+                        const size_t plane = (size_t)p.H * p.W;
+                        const size_t o = ((size_t)n * p.Co + c0) * plane + (size_t)gy * p.W + gx;
+                        if (p.out_fp32) {
+                            float* op = reinterpret_cast<float*>(p.out) + o;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < p.Co) op[(size_t)i * plane] = __uint_as_float(r[i]);
+                        } else {
+                            __half* op = reinterpret_cast<__half*>(p.out) + o;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < p.Co) op[(size_t)i * plane] = __float2half_rn(__uint_as_float(r[i]));
+                        }
+                    }
+                    continue;
+                }
+                if (valid && c0 < p.Co) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBias[c0 + i];
+                    const bool two = (c0 + 8) < p.Co;
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c0);
+                        const uint4 ra = __ldg(rp);
+                        const __half2* h = reinterpret_cast<const __half2*>(&ra);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(h[i]);
+                            v[2 * i] += f.x;
+                            v[2 * i + 1] += f.y;
+                        }
+                        if (two) {
+                            const uint4 rb = __ldg(rp + 1);
+                            const __half2* g = reinterpret_cast<const __half2*>(&rb);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(g[i]);
+                                v[8 + 2 * i] += f.x;
+                                v[8 + 2 * i + 1] += f.y;
+                            }
+                        }
+                    }
+                    uint4 o0, o1;
+                    __half2* ph0 = reinterpret_cast<__half2*>(&o0);
+                    __half2* ph1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ph0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        ph1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off + c0);
+                    op[0] = o0;
+                    if (two) op[1] = o1;
+                }
+            }
+        }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[ab]);
+        };
         int it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
@@ -285,83 +367,10 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_full);
             }
-            // ---- epilogue: accumulator row = pixel (mt = warp>>2, row = (warp&3)*32 + lane)
-            mbar_wait(&bars->tmem_full, it & 1);
-            tc_fence_after();
-            {
-                const int mt = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
-                const int chalf = warp >> 3;               // the two groups take alternate 16-column chunks
-                const int py = mt * 8 + (row >> 4), px = row & 15;
-                const int gy = ty * FP_T + py, gx = tx * FP_T + px;
-                const bool valid = gy < p.H && gx < p.W;
-                const size_t off = (((size_t)n * p.H + gy) * p.W + gx) * p.Co;
-                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + mt * p.n_tile;
-                uint32_t r[16];
-                for (int c0 = chalf * 16; c0 < p.n_tile; c0 += 32) {
-                    tc_ld16(taddr + c0, r);
-                    tc_wait_ld();
-                    if (HEAD) {
-                        if (valid) {
-                            const size_t plane = (size_t)p.H * p.W;
-                            const size_t o = ((size_t)n * p.Co + c0) * plane + (size_t)gy * p.W + gx;
-                            if (p.out_fp32) {
-                                float* op = reinterpret_cast<float*>(p.out) + o;
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (c0 + i < p.Co) op[(size_t)i * plane] = __uint_as_float(r[i]);
-                            } else {
-                                __half* op = reinterpret_cast<__half*>(p.out) + o;
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (c0 + i < p.Co) op[(size_t)i * plane] = __float2half_rn(__uint_as_float(r[i]));
-                            }
-                        }
-                        continue;
-                    }
-                    if (valid && c0 < p.Co) {
-                        float v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBias[c0 + i];
-                        const bool two = (c0 + 8) < p.Co;
-                        if (p.residual) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c0);
-                            const uint4 ra = __ldg(rp);
-                            const __half2* h = reinterpret_cast<const __half2*>(&ra);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float2 f = __half22float2(h[i]);
-                                v[2 * i] += f.x;
-                                v[2 * i + 1] += f.y;
-                            }
-                            if (two) {
-                                const uint4 rb = __ldg(rp + 1);
-                                const __half2* g = reinterpret_cast<const __half2*>(&rb);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 f = __half22float2(g[i]);
-                                    v[8 + 2 * i] += f.x;
-                                    v[8 + 2 * i + 1] += f.y;
-                                }
-                            }
-                        }
-                        uint4 o0, o1;
-                        __half2* ph0 = reinterpret_cast<__half2*>(&o0);
-                        __half2* ph1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            ph0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                            ph1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
-                        }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off + c0);
-                        op[0] = o0;
-                        if (two) op[1] = o1;
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty);
+            if (!HEAD) epilogue(t, it);
+            else if (it > 0) epilogue(t - (int)gridDim.x, it - 1);     // deferred: the MMAs of the previous tile retired long ago
         }
+        if (HEAD && it > 0) epilogue(blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
     }
 
     tc_fence_before();
@@ -490,7 +499,7 @@ extern "C" int lp_head_fused_f16(const void* a1, const void* a2, const void* dw_
                                  const void* pw_packed, void* out_nchw, int out_fp32, int N, int H, int W, int C1, int C2,
                                  int Co, lp_stream_t stream) {
     LP_CHECK_ARG(a1 && a2 && dw_cat && bdw_cat && pw_packed && out_nchw, "lp_head_fused_f16: null pointer");
-    LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 > 0 && Co > 0 && Co <= 160,
+    LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && C1 % 8 == 0 && C2 % 8 == 0 && C1 > 0 && C2 > 0 && Co > 0 && Co <= 128,
                  "lp_head_fused_f16: bad shape N=%d H=%d W=%d C1=%d C2=%d Co=%d", N, H, W, C1, C2, Co);
     if ((reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(a2) | reinterpret_cast<uintptr_t>(dw_cat) |
          reinterpret_cast<uintptr_t>(pw_packed)) & 15) {
