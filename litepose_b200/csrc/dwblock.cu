@@ -40,14 +40,15 @@ constexpr int BK_A_TILE = 128 * 64 * 2;
 constexpr int BK_DW_WARPS = 16;
 constexpr int BK_THREADS = (BK_DW_WARPS + 2) * 32;
 constexpr int BK_MAX_CE = 320;
-constexpr int BK_TMEM_E = 128;                    // first column of the expansion slots (2 x 128 columns)
+constexpr int BK_TMEM_E = 256;                    // first column of the expansion slots (2 x 128 columns); columns 0..255:
+                                                  // two projection accumulator buffers (2 M-tiles x n_tile <= 64 each)
 
 struct BkBars {
     uint64_t w_full;
     uint64_t x_full, x_empty;
     uint64_t e_full[2], e_empty[2];
     uint64_t a_full, a_empty;
-    uint64_t tmem_full, tmem_empty;
+    uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base, pad;
 };
 
@@ -95,8 +96,7 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->e_full[i], 1); mbar_init(&bars->e_empty[i], BK_DW_WARPS / 2); }
         mbar_init(&bars->a_full, BK_DW_WARPS);
         mbar_init(&bars->a_empty, 1);
-        mbar_init(&bars->tmem_full, 1);
-        mbar_init(&bars->tmem_empty, BK_DW_WARPS);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], BK_DW_WARPS); }
         fence_barrier_init();
     }
     if (warp == BK_DW_WARPS + 1) {
@@ -181,7 +181,7 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     }
                     // projection of K block kb
                     if (kb == 0) {
-                        mbar_wait_backoff(&bars->tmem_empty, (it & 1) ^ 1);
+                        mbar_wait_backoff(&bars->tmem_empty[it & 1], ((it >> 1) & 1) ^ 1);
                         tc_fence_after();
                     }
                     mbar_wait_backoff(&bars->a_full, kbc & 1);
@@ -191,12 +191,12 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     for (int mt = 0; mt < 2; ++mt) {
                         const uint32_t a_base = smem_u32(sA + mt * BK_A_TILE);
                         for (int k = 0; k < k16; ++k)
-                            tc_mma_f16(tmem_base + mt * p.n_tile, umma_desc_sw128(a_base + k * 32),
+                            tc_mma_f16(tmem_base + (it & 1) * 2 * p.n_tile + mt * p.n_tile, umma_desc_sw128(a_base + k * 32),
                                        umma_desc_sw128(b_base + k * 32), idesc_p, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&bars->a_empty);
                 }
-                tc_commit(&bars->tmem_full);
+                tc_commit(&bars->tmem_full[it & 1]);
             }
         }
     } else {
@@ -214,6 +214,69 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         uint8_t* slab = sSlab + grp * BK_SLAB;
         uint32_t ec = 0, kbc = 0;
         int it = 0;
+        // ---- final epilogue of tile te (iteration ite), DEFERRED: it runs after the first K block of the next tile has
+        // been handed to the tensor cores, so the depthwise warps never wait for the last projection MMAs of a tile (two
+        // accumulator buffers).  accumulator row = pixel (mt = warp>>2 & 1, row = (warp&3)*32 + lane)
+        auto epilogue = [&](int te, int ite) {
+            const int tx = te % p.tiles_x, ty = (te / p.tiles_x) % p.tiles_y, n = te / (p.tiles_x * p.tiles_y);
+            mbar_wait(&bars->tmem_full[ite & 1], (ite >> 1) & 1);
+            tc_fence_after();
+        {
+            const int mt = (warp >> 2) & 1, row = q * 32 + lane;
+            const int chalf = warp >> 3;               // the two groups take alternate 16-column chunks
+            const int py = mt * 8 + (row >> 4), px = row & 15;
+            const int gy = ty * BK_T + py, gx = tx * BK_T + px;
+            const bool valid = gy < p.H && gx < p.W;
+            const size_t off = (((size_t)n * p.H + gy) * p.W + gx) * p.Co;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (ite & 1) * 2 * p.n_tile + mt * p.n_tile;
+            uint32_t r[16];
+            for (int c0 = chalf * 16; c0 < p.n_tile; c0 += 32) {
+                tc_ld16(taddr + c0, r);
+                tc_wait_ld();
+                if (valid && c0 < p.Co) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBpj[c0 + i];
+                    const bool two = (c0 + 8) < p.Co;
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c0);
+                        const uint4 ra = __ldg(rp);
+                        const __half2* h = reinterpret_cast<const __half2*>(&ra);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(h[i]);
+                            v[2 * i] += f.x;
+                            v[2 * i + 1] += f.y;
+                        }
+                        if (two) {
+                            const uint4 rb = __ldg(rp + 1);
+                            const __half2* g = reinterpret_cast<const __half2*>(&rb);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(g[i]);
+                                v[8 + 2 * i] += f.x;
+                                v[8 + 2 * i + 1] += f.y;
+                            }
+                        }
+                    }
+                    uint4 o0, o1;
+                    __half2* ph0 = reinterpret_cast<__half2*>(&o0);
+                    __half2* ph1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ph0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        ph1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(p.out + off + c0);
+                    op[0] = o0;
+                    if (two) op[1] = o1;
+                }
+            }
+        }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[ite & 1]);
+        };
         mbar_wait(&bars->w_full, 0);                       // depthwise weights resident
         pdl_wait();                                        // the identity rows are read from global memory
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -299,66 +362,10 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_full);
+                if (kb == 0 && it > 0) epilogue(t - (int)gridDim.x, it - 1);
             }
-            // ---- final epilogue: accumulator row = pixel (mt = warp>>2 & 1, row = (warp&3)*32 + lane)
-            mbar_wait(&bars->tmem_full, it & 1);
-            tc_fence_after();
-            {
-                const int mt = (warp >> 2) & 1, row = q * 32 + lane;
-                const int chalf = warp >> 3;               // the two groups take alternate 16-column chunks
-                const int py = mt * 8 + (row >> 4), px = row & 15;
-                const int gy = ty * BK_T + py, gx = tx * BK_T + px;
-                const bool valid = gy < p.H && gx < p.W;
-                const size_t off = (((size_t)n * p.H + gy) * p.W + gx) * p.Co;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + mt * p.n_tile;
-                uint32_t r[16];
-                for (int c0 = chalf * 16; c0 < p.n_tile; c0 += 32) {
-                    tc_ld16(taddr + c0, r);
-                    tc_wait_ld();
-                    if (valid && c0 < p.Co) {
-                        float v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBpj[c0 + i];
-                        const bool two = (c0 + 8) < p.Co;
-                        if (p.residual) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c0);
-                            const uint4 ra = __ldg(rp);
-                            const __half2* h = reinterpret_cast<const __half2*>(&ra);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float2 f = __half22float2(h[i]);
-                                v[2 * i] += f.x;
-                                v[2 * i + 1] += f.y;
-                            }
-                            if (two) {
-                                const uint4 rb = __ldg(rp + 1);
-                                const __half2* g = reinterpret_cast<const __half2*>(&rb);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 f = __half22float2(g[i]);
-                                    v[8 + 2 * i] += f.x;
-                                    v[8 + 2 * i + 1] += f.y;
-                                }
-                            }
-                        }
-                        uint4 o0, o1;
-                        __half2* ph0 = reinterpret_cast<__half2*>(&o0);
-                        __half2* ph1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            ph0[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                            ph1[i] = __floats2half2_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
-                        }
-                        uint4* op = reinterpret_cast<uint4*>(p.out + off + c0);
-                        op[0] = o0;
-                        if (two) op[1] = o1;
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty);
         }
+        if (it > 0) epilogue((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
     }
 
     tc_fence_before();
