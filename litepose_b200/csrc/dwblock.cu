@@ -143,8 +143,11 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint32_t ecount[2] = {0, 0};          // expansion jobs issued per group
             mbar_wait_backoff(&bars->w_full, 0);
             // expansion of slab s of the tile whose X is resident; group = s & 1
-            auto expand = [&](int s, bool last_of_tile) {
-                const int g = s & 1;
+            // Odd slab counts (Ce = 96: 3 slabs) leave one group idle in the last round of a tile; the groups therefore swap
+            // roles on odd tiles (group 0 takes the odd slabs), so that over two tiles each group runs the same number of
+            // slabs and - the groups being only loosely coupled through the A tile - both stay busy.
+            auto expand = [&](int s, bool last_of_tile, int tile_it) {
+                const int g = (s & 1) ^ ((p.nslabs & 1) ? (tile_it & 1) : 0);
                 mbar_wait_backoff(&bars->e_empty[g], (ecount[g] & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t b_base = smem_u32(sWe + s * BK_WE_SLAB);
@@ -162,8 +165,8 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (my_tiles > 0) {
                 mbar_wait_backoff(&bars->x_full, 0);
                 tc_fence_after();
-                expand(0, p.nslabs == 1);
-                if (p.nslabs > 1) expand(1, p.nslabs == 2);
+                expand(0, p.nslabs == 1, 0);
+                if (p.nslabs > 1) expand(1, p.nslabs == 2, 0);
             }
             for (; it < my_tiles; ++it) {
                 for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
@@ -171,13 +174,13 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     // for the groups' epilogue-1 of the current slabs, which precedes the depthwise work awaited below
                     if (kb + 1 < p.nkb) {
                         const int s0 = 2 * (kb + 1);
-                        expand(s0, s0 == p.nslabs - 1);
-                        if (s0 + 1 < p.nslabs) expand(s0 + 1, s0 + 1 == p.nslabs - 1);
+                        expand(s0, s0 == p.nslabs - 1, it);
+                        if (s0 + 1 < p.nslabs) expand(s0 + 1, s0 + 1 == p.nslabs - 1, it);
                     } else if (it + 1 < my_tiles) {
                         mbar_wait_backoff(&bars->x_full, (it + 1) & 1);
                         tc_fence_after();
-                        expand(0, p.nslabs == 1);
-                        if (p.nslabs > 1) expand(1, p.nslabs == 2);
+                        expand(0, p.nslabs == 1, it + 1);
+                        if (p.nslabs > 1) expand(1, p.nslabs == 2, it + 1);
                     }
                     // projection of K block kb
                     if (kb == 0) {
@@ -292,7 +295,8 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 if (pi < BK_PIX && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) inside |= 1u << mt;
             }
             for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
-                const int s = 2 * kb + grp;
+                const int vg = grp ^ ((p.nslabs & 1) ? (it & 1) : 0);      // which slab parity this group runs in this tile
+                const int s = 2 * kb + vg;
                 const bool have = s < p.nslabs;
                 __half2 acch[4][4];
                 if (have) {
@@ -357,7 +361,7 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 // the single A buffer is free once the MMAs of the previous K block have retired
                 mbar_wait(&bars->a_empty, (kbc & 1) ^ 1);
                 if (have) {
-                    dw_store_a<4>(sA, BK_A_TILE, acch, oy, ox, mir, (grp << 2) | (cp >> 2), cp);
+                    dw_store_a<4>(sA, BK_A_TILE, acch, oy, ox, mir, (vg << 2) | (cp >> 2), cp);
                     fence_proxy_async();
                 }
                 __syncwarp();
