@@ -13,11 +13,14 @@
 //                rounds), including its `abs(t) < 1e-2` which binds to int abs(int) with its includes: trunc(t) == 0.
 // The reference's [10] stack arrays (assign.cpp:46-48,79-80) are lifted to 32 entries; its unbounded KM loop is capped
 // (status 1 is reported where the reference would not return).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lp {
 
 constexpr int FU_MAXP = 32;
+constexpr int FU_MAXPAIRS = 256;
 constexpr int FU_MAX_ROUNDS = 1 << 20;   // per KM row; the reference needs ~1e4/|d| rounds to reach a padded column
 constexpr int FP_THREADS = 256;
 constexpr int FP_PPT = 4;
@@ -102,12 +105,15 @@ struct FuShared {
     float diff[FU_MAXP][FU_MAXP + 1];
     float sum[FU_MAXP];
     int ch[FU_MAXP], nj[FU_MAXP];
+    int npairs;
+    unsigned short pairs[FU_MAXPAIRS];     // fast-forward: row | column << 5 | tree-edge flag << 10
 };
 
 struct FuKm {
     float Lx, Ly, slack;
     int mat;
     unsigned S, T;
+    unsigned ev, tr;     // per column lane: rows whose pair with this column the last search evaluated as non-tight / took as tree edge
 };
 
 __device__ __forceinline__ float fu_min(float a, float b) { return a < b ? a : b; }   // the reference's MIN macro
@@ -130,13 +136,20 @@ __device__ bool fu_match(const FuShared& s, FuKm& k, int n, int u0, int lane) {
         const bool active = lane < n && lane >= pos && !((k.T >> lane) & 1u);
         const unsigned eq = __ballot_sync(0xffffffffu, active && __float2int_rz(t) == 0);
         if (eq == 0) {
-            if (active) k.slack = fu_min(k.slack, t);
+            if (active) {
+                k.slack = fu_min(k.slack, t);
+                k.ev |= 1u << u;
+            }
             if (sp == 0) return false;
             --sp;                         // the caller resumes behind the column it descended from
             continue;
         }
         const int e = __ffs(eq) - 1;
-        if (active && lane < e) k.slack = fu_min(k.slack, t);
+        if (active && lane < e) {
+            k.slack = fu_min(k.slack, t);
+            k.ev |= 1u << u;
+        }
+        if (lane == e) k.tr |= 1u << u;
         k.T |= 1u << e;
         const int m = __shfl_sync(0xffffffffu, k.mat, e);
         if (m == -1) {
@@ -156,7 +169,7 @@ __device__ bool fu_match(const FuShared& s, FuKm& k, int n, int u0, int lane) {
 }
 
 // assign.cpp:45-66; false when the round cap is hit (the reference has none)
-__device__ bool fu_km(FuShared& s, int n, int lane) {
+__device__ bool fu_km(FuShared& s, int n, int lane, bool ff) {
     FuKm k;
     k.Lx = -1e6f;
     if (lane < n)
@@ -167,9 +180,12 @@ __device__ bool fu_km(FuShared& s, int n, int lane) {
     for (int i = 0; i < n; ++i) {
         k.slack = 1e6f;
         int rounds = 0;
+        unsigned prevS = 0xffffffffu, prevT = 0xffffffffu;
         for (;;) {
             k.S = 0;
             k.T = 0;
+            k.ev = 0;
+            k.tr = 0;
             if (fu_match(s, k, n, i, lane)) break;
             if (++rounds >= FU_MAX_ROUNDS) return false;
             float d = lane < n ? fu_min(1e8f, k.slack) : 1e8f;           // assign.cpp:33-43
@@ -177,6 +193,100 @@ __device__ bool fu_km(FuShared& s, int n, int lane) {
             for (int o = 16; o > 0; o >>= 1) d = fu_min(d, __shfl_xor_sync(0xffffffffu, d, o));
             if ((k.S >> lane) & 1u) k.Lx = __fsub_rn(k.Lx, d);
             if ((k.T >> lane) & 1u) k.Ly = __fadd_rn(k.Ly, d);
+
+            // ---- fast-forward of a label walk (round 2).  d often stems from a pair whose column has been visited since
+            // (slack is only reset per row), while the only unvisited columns left are far away (a padded -1e4 column):
+            // the labels then crawl for thousands of rounds with the SAME failed search.  A round can be skipped - its label
+            // update applied without running the search - iff the search would evaluate the same pairs with the same
+            // tight / non-tight outcome.  The search consults only the pairs it evaluated last time (ev: non-tight, feeds
+            // slack; tr: tree edge, tight), so:
+            //   * pairs with a visited column only drift by rounding: they are re-evaluated EXACTLY every skipped round
+            //     (same fp32 expression), their minimum keeps the running slack minimum exact (only the minimum over all
+            //     columns is ever consumed), a status flip ends the walk before that round is skipped;
+            //   * pairs with an unvisited column drop by at most d + DELTA per round: a conservative bound on the number of
+            //     rounds for which they stay non-tight and >= d is computed once.
+            const bool walk = ff && (k.S == prevS) && (k.T == prevT) && d > 0.f;
+            prevS = k.S;
+            prevT = k.T;
+            if (walk) {
+                constexpr float DELTA = 0.008f;           // rounding drift bound per round for |labels| < 1e5
+                const bool inS = (k.S >> lane) & 1u, inT = (k.T >> lane) & 1u;
+                // (1) conservative round bound from the evaluated pairs with an unvisited column
+                float rl = (lane >= n || (fabsf(k.Lx) < 1e5f && fabsf(k.Ly) < 1e5f)) ? 1e9f : 0.f;
+                for (unsigned sb = k.S; sb; sb &= sb - 1) {
+                    const int u = __ffs(sb) - 1;
+                    const float lxu = __shfl_sync(0xffffffffu, k.Lx, u);
+                    if (lane < n && !inT && ((k.ev >> u) & 1u)) {
+                        const float t = __fsub_rn(__fadd_rn(lxu, k.Ly), s.G[u][lane]);
+                        const float x = (t - fmaxf(1.f, d) - 2.f * DELTA) / (d + DELTA);
+                        rl = fu_min(rl, x >= 0.f ? floorf(x) + 1.f : 0.f);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rl = fu_min(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+                int rmax = rl > 1e6f ? 1000000 : (int)rl;
+                if (rmax > FU_MAX_ROUNDS - 1 - rounds) rmax = FU_MAX_ROUNDS - 1 - rounds;
+                // (2) list of the pairs that are tracked exactly: visited column, evaluated (type 0) or tree edge (type 1)
+                if (lane == 0) s.npairs = 0;
+                __syncwarp();
+                if (lane < n && inT) {
+                    for (unsigned m = k.ev | k.tr; m; m &= m - 1) {
+                        const int u = __ffs(m) - 1;
+                        const int q = atomicAdd(&s.npairs, 1);
+                        if (q < FU_MAXPAIRS) s.pairs[q] = (unsigned short)(u | (lane << 5) | (((k.tr >> u) & 1u) << 10));
+                    }
+                }
+                __syncwarp();
+                const int np = s.npairs;
+                if (np <= FU_MAXPAIRS) {
+                    float gmin = d;                       // running minimum of slack over all columns (== d after the reduction)
+                    // the first 32 tracked pairs live in registers (pair q <-> lane q); more (rare) are re-read from smem
+                    const unsigned e0 = lane < np ? s.pairs[lane] : 0u;
+                    const int u0 = e0 & 31, v0 = (e0 >> 5) & 31;
+                    const float g0 = s.G[u0][v0];
+                    const bool have0 = lane < np, tree0 = (e0 >> 10) & 1u;
+                    for (int j = 0; j < rmax; ++j) {
+                        // the search on the current labels: exact re-evaluation of the tracked pairs
+                        float tmin = 1e30f;
+                        bool flip = false;
+                        {
+                            const float lxu = __shfl_sync(0xffffffffu, k.Lx, u0);
+                            const float lyv = __shfl_sync(0xffffffffu, k.Ly, v0);
+                            const float t = __fsub_rn(__fadd_rn(lxu, lyv), g0);
+                            const bool tight = __float2int_rz(t) == 0;
+                            if (have0) {
+                                flip = tree0 ? !tight : tight;
+                                if (!tree0) tmin = t;
+                            }
+                        }
+                        for (int q0 = 32; q0 < np; q0 += 32) {
+                            const int q = q0 + lane;
+                            const unsigned e = q < np ? s.pairs[q] : 0u;
+                            const int u = e & 31, v = (e >> 5) & 31;
+                            const float lxu = __shfl_sync(0xffffffffu, k.Lx, u);
+                            const float lyv = __shfl_sync(0xffffffffu, k.Ly, v);
+                            if (q < np) {
+                                const float t = __fsub_rn(__fadd_rn(lxu, lyv), s.G[u][v]);
+                                const bool tight = __float2int_rz(t) == 0;
+                                if ((e >> 10) & 1u) flip |= !tight;
+                                else {
+                                    flip |= tight;
+                                    tmin = fu_min(tmin, t);
+                                }
+                            }
+                        }
+                        if (__any_sync(0xffffffffu, flip)) break;      // this state needs the real search
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) tmin = fu_min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+                        if (tmin <= 0.f) break;
+                        gmin = fu_min(gmin, tmin);
+                        ++rounds;
+                        if (inS) k.Lx = __fsub_rn(k.Lx, gmin);
+                        if (inT) k.Ly = __fadd_rn(k.Ly, gmin);
+                    }
+                    if (lane == 0) k.slack = fu_min(k.slack, gmin);     // only the minimum over the columns is ever consumed
+                }
+            }
         }
     }
     if (lane < n) s.ch[k.mat] = lane;
@@ -187,7 +297,7 @@ __device__ bool fu_km(FuShared& s, int n, int lane) {
 __global__ void __launch_bounds__(32)
 assign_kernel(const int* __restrict__ count, const float* __restrict__ val, const float* __restrict__ tag,
               const int* __restrict__ ind, const int* __restrict__ joint_order, int C, int M, float threshold,
-              int* __restrict__ num_person, float* __restrict__ ans, int* __restrict__ status) {
+              int* __restrict__ num_person, float* __restrict__ ans, int* __restrict__ status, int ff) {
     __shared__ FuShared s;
     const int img = blockIdx.x, lane = threadIdx.x;
     const int* cnt = count + (size_t)img * C;
@@ -232,7 +342,7 @@ assign_kernel(const int* __restrict__ count, const float* __restrict__ val, cons
             }
         }
         __syncwarp();
-        if (!fu_km(s, n, lane)) {
+        if (!fu_km(s, n, lane, ff != 0)) {
             st = 1;
             break;
         }
@@ -296,8 +406,13 @@ extern "C" int lp_assign_f32(const int* count, const float* val, const float* ta
         set_error("lp_assign_f32: max_count %d exceeds the %d candidates/persons this build holds per joint", M, FU_MAXP);
         return LP_ERR_CAPACITY;
     }
+    static int ff = -1;
+    if (ff < 0) {
+        const char* e = getenv("LP_FU_FASTFORWARD");     // ablation switch; default on
+        ff = (e && e[0] == '0') ? 0 : 1;
+    }
     assign_kernel<<<N, 32, 0, (cudaStream_t)stream>>>(count, val, tag, ind, joint_order, C, M, threshold, num_person, ans,
-                                                     status);
+                                                     status, ff);
     LP_LAUNCH_CHECK("assign_kernel");
     return LP_OK;
 }

@@ -107,3 +107,27 @@ def test_group_parser_mirror():
     ref0 = exp[0][1][:exp[0][0]].copy()
     ref0[:, :, :2] *= 4.0
     assert np.array_equal(one.cpu().numpy(), ref0)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_assign_label_walks_randomised(seed):
+    """Round 2: the KM kernel skips rounds of a label walk (same failed search, labels crawling towards a padded column) by
+    re-evaluating only the pairs the search looks at - the result must stay bit-identical to the round-by-round C
+    restatement.  Cases with missing joints (long walks), close tags (small d), clutter and plateaus."""
+    rs = np.random.RandomState(seed)
+    people = int(rs.randint(2, 14))
+    det, tm = cases.make_case(7000 + seed, n=3, people=people, spread=float(rs.choice([0.3, 0.6, 2.0])),
+                              tagnoise=float(rs.choice([0.02, 0.2, 0.6])), plateau=bool(seed & 1), clutter=int(rs.randint(0, 25)),
+                              h=64, w=56)
+    m = int(rs.choice([16, 30]))
+    exp = fu.find_peaks(det, tm, 0.1, 5, m, "port")
+    got = plugins.find_peaks(_dev(det), _dev(tm), 0.1, 5, m)
+    jo = torch.tensor(cases.JOINT_ORDER_17, dtype=torch.int32, device="cuda")
+    tthr = float(rs.choice([0.5, 1.0, 2.0]))
+    num, ans = plugins.assign(*got, jo, tthr, m)
+    st = plugins.last_status().cpu().numpy()
+    for i in range(det.shape[0]):
+        n1, a1, s1 = fu.assign(exp[0][i], exp[1][i], exp[2][i], exp[3][i], cases.JOINT_ORDER_17, tthr, m, "port")
+        assert s1 == st[i]
+        if s1 == 0:
+            assert n1 == int(num[i]) and np.array_equal(a1, ans[i].cpu().numpy()), (seed, i)
