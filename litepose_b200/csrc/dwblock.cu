@@ -39,12 +39,16 @@ constexpr int BK_DW_SLAB = 3200;                 // their pitch in shared memory
 constexpr int BK_A_TILE = 128 * 64 * 2;
 constexpr int BK_DW_WARPS = 16;
 constexpr int BK_THREADS = (BK_DW_WARPS + 2) * 32;
-constexpr int BK_MAX_CE = 320;
+constexpr int BK_MAX_CE = 416;
 constexpr int BK_TMEM_E = 256;                    // first column of the expansion slots (2 x 128 columns); columns 0..255:
                                                   // two projection accumulator buffers (2 M-tiles x n_tile <= 64 each)
 
 struct BkBars {
     uint64_t w_full;
+    // streaming mode (the three weight sets do not fit beside X and the slabs): two-slot rings
+    uint64_t we_full[2], we_empty[2];          // expansion weights of a slab: producer -> MMA issuer
+    uint64_t dw_full[2][2], dw_empty[2][2];    // depthwise weights of a slab, per group: producer -> the group's warps
+    uint64_t wp_full[2], wp_empty[2];          // projection weights of a K block: producer -> MMA issuer
     uint64_t x_full, x_empty;
     uint64_t e_full[2], e_empty[2];
     uint64_t a_full, a_empty;
@@ -57,6 +61,7 @@ struct BkParams {
     int tiles_x, tiles_y, num_tiles;
     int nslabs, nkb, k16;             // k16 = K=16 MMA steps that carry input channels (ceil(Cin/16))
     int off_we, off_slab, off_dww, off_a, off_wp, off_bias;   // shared-memory layout (bytes)
+    int wp_stage;                     // streaming mode: bytes of one projection-weight ring slot
     int skew_ns;                      // group 1 starts every tile this much later (phase offset of the two groups)
     const float* b_exp;               // [Ce]
     const float* b_dw;                // [Ce]
@@ -65,7 +70,9 @@ struct BkParams {
     __half* out;                      // [N,H,W,Co]
 };
 
-template <int DUMMY>
+// STREAM = 0: all weights of the block resident in shared memory; STREAM = 1: expansion / depthwise / projection weights
+// travel through two-slot rings (blocks with Ce up to 288 at Cin = 48: stage 2 of LitePose-S)
+template <int STREAM>
 __global__ void __launch_bounds__(BK_THREADS, 1)
 block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_we,
                 const __grid_constant__ CUtensorMap map_dw, const __grid_constant__ CUtensorMap map_wp,
@@ -91,6 +98,13 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tma_prefetch_desc(&map_dw);
         tma_prefetch_desc(&map_wp);
         mbar_init(&bars->w_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->we_full[i], 1);
+            mbar_init(&bars->we_empty[i], 1);
+            mbar_init(&bars->wp_full[i], 1);
+            mbar_init(&bars->wp_empty[i], 1);
+            for (int g = 0; g < 2; ++g) { mbar_init(&bars->dw_full[g][i], 1); mbar_init(&bars->dw_empty[g][i], BK_DW_WARPS / 2); }
+        }
         mbar_init(&bars->x_full, 1);
         mbar_init(&bars->x_empty, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->e_full[i], 1); mbar_init(&bars->e_empty[i], BK_DW_WARPS / 2); }
@@ -117,21 +131,54 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (warp == BK_DW_WARPS) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            // weights are static: they may be fetched before the previous kernel of the stream has finished
-            mbar_expect_tx(&bars->w_full, (uint32_t)(p.nslabs * (BK_WE_SLAB + BK_DW_BYTES) + p.nkb * p.n_tile * 128));
-            for (int s = 0; s < p.nslabs; ++s) {
-                tma_load_2d(sWe + s * BK_WE_SLAB, &map_we, &bars->w_full, 0, s * BK_CB);
-                tma_load_2d(sDww + s * BK_DW_SLAB, &map_dw, &bars->w_full, s * BK_CB, 0);
+            if (!STREAM) {
+                // weights are static: they may be fetched before the previous kernel of the stream has finished
+                mbar_expect_tx(&bars->w_full, (uint32_t)(p.nslabs * (BK_WE_SLAB + BK_DW_BYTES) + p.nkb * p.n_tile * 128));
+                for (int s = 0; s < p.nslabs; ++s) {
+                    tma_load_2d(sWe + s * BK_WE_SLAB, &map_we, &bars->w_full, 0, s * BK_CB);
+                    tma_load_2d(sDww + s * BK_DW_SLAB, &map_dw, &bars->w_full, s * BK_CB, 0);
+                }
+                for (int kb = 0; kb < p.nkb; ++kb)
+                    tma_load_2d(sWp + kb * p.n_tile * 128, &map_wp, &bars->w_full, 0, kb * p.n_tile);
             }
-            for (int kb = 0; kb < p.nkb; ++kb)
-                tma_load_2d(sWp + kb * p.n_tile * 128, &map_wp, &bars->w_full, 0, kb * p.n_tile);
             pdl_wait();               // the block input is complete from here on
+            uint32_t we_n = 0, wp_n = 0, dw_n[2] = {0, 0};
             int it = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
                 const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
                 mbar_wait_backoff(&bars->x_empty, (it & 1) ^ 1);
                 mbar_expect_tx(&bars->x_full, BK_X_TX);
                 tma_load_4d(sX, &map_x, &bars->x_full, 0, tx * BK_T - 3, ty * BK_T - 3, n);
+                if (STREAM) {
+                    // the tile's weights in the order their consumers want them: per K block the expansion weights of its
+                    // slabs (MMA issuer, slab order), their depthwise weights (the group that runs the slab), then the
+                    // projection weights of the K block; two-slot rings keep the producer about one K block ahead
+                    const int sw = (p.nslabs & 1) ? (it & 1) : 0;
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        for (int s = 2 * kb; s < 2 * kb + 2 && s < p.nslabs; ++s) {
+                            const uint32_t q = we_n & 1;
+                            mbar_wait_backoff(&bars->we_empty[q], ((we_n >> 1) & 1) ^ 1);
+                            mbar_expect_tx(&bars->we_full[q], BK_WE_SLAB);
+                            tma_load_2d(sWe + q * BK_WE_SLAB, &map_we, &bars->we_full[q], 0, s * BK_CB);
+                            ++we_n;
+                        }
+                        for (int s = 2 * kb; s < 2 * kb + 2 && s < p.nslabs; ++s) {
+                            const int g = (s & 1) ^ sw;
+                            const uint32_t q = dw_n[g] & 1;
+                            mbar_wait_backoff(&bars->dw_empty[g][q], ((dw_n[g] >> 1) & 1) ^ 1);
+                            mbar_expect_tx(&bars->dw_full[g][q], BK_DW_BYTES);
+                            tma_load_2d(sDww + (g * 2 + q) * BK_DW_SLAB, &map_dw, &bars->dw_full[g][q], s * BK_CB, 0);
+                            ++dw_n[g];
+                        }
+                        {
+                            const uint32_t q = wp_n & 1;
+                            mbar_wait_backoff(&bars->wp_empty[q], ((wp_n >> 1) & 1) ^ 1);
+                            mbar_expect_tx(&bars->wp_full[q], (uint32_t)p.n_tile * 128);
+                            tma_load_2d(sWp + q * p.wp_stage, &map_wp, &bars->wp_full[q], 0, kb * p.n_tile);
+                            ++wp_n;
+                        }
+                    }
+                }
             }
         }
     } else if (warp == BK_DW_WARPS + 1) {
@@ -141,7 +188,8 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint32_t idesc_p = umma_idesc_f16(128, p.n_tile);
             const uint32_t x_base = smem_u32(sX);
             uint32_t ecount[2] = {0, 0};          // expansion jobs issued per group
-            mbar_wait_backoff(&bars->w_full, 0);
+            if (!STREAM) mbar_wait_backoff(&bars->w_full, 0);
+            uint32_t we_c = 0, wp_c = 0;
             // expansion of slab s of the tile whose X is resident; group = s & 1
             // Odd slab counts (Ce = 96: 3 slabs) leave one group idle in the last round of a tile; the groups therefore swap
             // roles on odd tiles (group 0 takes the odd slabs), so that over two tiles each group runs the same number of
@@ -150,12 +198,21 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const int g = (s & 1) ^ ((p.nslabs & 1) ? (tile_it & 1) : 0);
                 mbar_wait_backoff(&bars->e_empty[g], (ecount[g] & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t b_base = smem_u32(sWe + s * BK_WE_SLAB);
+                uint32_t b_base = smem_u32(sWe + s * BK_WE_SLAB);
+                if (STREAM) {
+                    mbar_wait_backoff(&bars->we_full[we_c & 1], (we_c >> 1) & 1);
+                    tc_fence_after();
+                    b_base = smem_u32(sWe + (we_c & 1) * BK_WE_SLAB);
+                }
                 for (int mt = 0; mt < 4; ++mt)
                     for (int k = 0; k < p.k16; ++k)
                         tc_mma_f16(tmem_base + BK_TMEM_E + g * 128 + mt * BK_CB, umma_desc_sw128(x_base + mt * 16384 + k * 32),
                                    umma_desc_sw128(b_base + k * 32), idesc_e, k > 0 ? 1u : 0u);
                 tc_commit(&bars->e_full[g]);
+                if (STREAM) {
+                    tc_commit(&bars->we_empty[we_c & 1]);
+                    ++we_c;
+                }
                 if (last_of_tile) tc_commit(&bars->x_empty);     // X may be overwritten once these MMAs have retired
                 ++ecount[g];
             };
@@ -190,7 +247,12 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     mbar_wait_backoff(&bars->a_full, kbc & 1);
                     tc_fence_after();
                     const int k16 = 2 * min(2, p.nslabs - 2 * kb);
-                    const uint32_t b_base = smem_u32(sWp + kb * p.n_tile * 128);
+                    uint32_t b_base = smem_u32(sWp + kb * p.n_tile * 128);
+                    if (STREAM) {
+                        mbar_wait_backoff(&bars->wp_full[wp_c & 1], (wp_c >> 1) & 1);
+                        tc_fence_after();
+                        b_base = smem_u32(sWp + (wp_c & 1) * p.wp_stage);
+                    }
                     for (int mt = 0; mt < 2; ++mt) {
                         const uint32_t a_base = smem_u32(sA + mt * BK_A_TILE);
                         for (int k = 0; k < k16; ++k)
@@ -198,6 +260,10 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                                        umma_desc_sw128(b_base + k * 32), idesc_p, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&bars->a_empty);
+                    if (STREAM) {
+                        tc_commit(&bars->wp_empty[wp_c & 1]);
+                        ++wp_c;
+                    }
                 }
                 tc_commit(&bars->tmem_full[it & 1]);
             }
@@ -280,7 +346,7 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[ite & 1]);
         };
-        mbar_wait(&bars->w_full, 0);                       // depthwise weights resident
+        if (!STREAM) mbar_wait(&bars->w_full, 0);           // depthwise weights resident
         pdl_wait();                                        // the identity rows are read from global memory
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
@@ -355,8 +421,18 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const int ch = s * BK_CB + 2 * cp;
                     const __half2 bh = __float22half2_rn(*reinterpret_cast<const float2*>(sBdw + ch));
                     const __half2* tile_in = reinterpret_cast<const __half2*>(slab + (cp >> 2) * BK_CHUNK) + (cp & 3);
-                    dw_slab_hfma2<K, 4, BK_I, BK_CB, 4>(tile_in, reinterpret_cast<const __half2*>(sDww + s * BK_DW_SLAB), cp, mir,
-                                                        oy, ox, bh, acch);
+                    if (STREAM) {
+                        // this slab's depthwise weights arrive through the group's ring (slot = slabs run by the group so far)
+                        const uint32_t q = (ec - 1) & 1;
+                        mbar_wait(&bars->dw_full[grp][q], ((ec - 1) >> 1) & 1);
+                        dw_slab_hfma2<K, 4, BK_I, BK_CB, 4>(tile_in, reinterpret_cast<const __half2*>(sDww + (grp * 2 + q) * BK_DW_SLAB),
+                                                            cp, mir, oy, ox, bh, acch);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->dw_empty[grp][q]);
+                    } else {
+                        dw_slab_hfma2<K, 4, BK_I, BK_CB, 4>(tile_in, reinterpret_cast<const __half2*>(sDww + s * BK_DW_SLAB), cp, mir,
+                                                            oy, ox, bh, acch);
+                    }
                 }
                 // the single A buffer is free once the MMAs of the previous K block have retired
                 mbar_wait(&bars->a_empty, (kbc & 1) ^ 1);
@@ -380,13 +456,15 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
 }
 
-static size_t bk_layout(BkParams& p) {
+static size_t bk_layout(BkParams& p, int stream) {
     size_t off = BK_X_BYTES;
-    p.off_we = (int)off;                       off += (size_t)p.nslabs * BK_WE_SLAB;         // 1024-aligned (4 KiB slabs)
+    const int n_we = stream ? 2 : p.nslabs, n_dw = stream ? 4 : p.nslabs;
+    p.wp_stage = (p.n_tile * 128 + 1023) & ~1023;
+    p.off_we = (int)off;                       off += (size_t)n_we * BK_WE_SLAB;             // 1024-aligned (4 KiB slabs)
     p.off_a = (int)off;                        off += 2 * BK_A_TILE;                          // 1024-aligned
-    p.off_wp = (int)off;                       off += ((size_t)p.nkb * p.n_tile * 128 + 1023) & ~(size_t)1023;
+    p.off_wp = (int)off;                       off += stream ? (size_t)2 * p.wp_stage : (((size_t)p.nkb * p.n_tile * 128 + 1023) & ~(size_t)1023);
     p.off_slab = (int)off;                     off += 2 * BK_SLAB;
-    p.off_dww = (int)off;                      off += ((size_t)p.nslabs * BK_DW_SLAB + 127) & ~(size_t)127;
+    p.off_dww = (int)off;                      off += ((size_t)n_dw * BK_DW_SLAB + 127) & ~(size_t)127;
     p.off_bias = (int)off;                     off += (2 * BK_MAX_CE + 64) * 4 + sizeof(BkBars) + 64;
     return off + 1024;                         // alignment slack of the dynamic shared-memory base
 }
@@ -395,7 +473,7 @@ static size_t bk_layout(BkParams& p) {
 
 using namespace lp;
 
-static int bk_shape_ok(int Cin, int Ce, int Co, BkParams* out) {
+static int bk_shape_ok(int Cin, int Ce, int Co, BkParams* out, int* stream_out = nullptr) {
     if (Cin < 8 || Cin > 64 || Cin % 8 || Ce < 8 || Ce % 8 || Ce > BK_MAX_CE - BK_CB || Co < 8 || Co % 8 || Co > 64) return 0;
     BkParams p;
     memset(&p, 0, sizeof(p));
@@ -404,9 +482,15 @@ static int bk_shape_ok(int Cin, int Ce, int Co, BkParams* out) {
     p.nslabs = (Ce + BK_CB - 1) / BK_CB;
     p.nkb = (Ce + 63) / 64;
     p.k16 = (Cin + 15) / 16;
-    const size_t need = bk_layout(p);
-    if (need > 232448) return 0;                 // 227 KiB of dynamic shared memory per CTA on sm_100
+    int stream = 0;
+    size_t need = bk_layout(p, 0);               // everything resident when it fits (no ring hand-overs)
+    if (need > 232448) {                         // 227 KiB of dynamic shared memory per CTA on sm_100
+        stream = 1;
+        need = bk_layout(p, 1);
+        if (need > 232448) return 0;
+    }
     if (out) *out = p;
+    if (stream_out) *stream_out = stream;
     return (int)need;
 }
 
@@ -430,7 +514,8 @@ extern "C" int lp_block_s1_f16(const void* x, const void* w_exp_packed, const fl
                                void* out, int N, int H, int W, int Cin, int Ce, int Co, lp_stream_t stream) {
     LP_CHECK_ARG(x && w_exp_packed && w_dw && w_proj_packed && out, "lp_block_s1_f16: null pointer");
     BkParams p;
-    const int need = bk_shape_ok(Cin, Ce, Co, &p);
+    int stream_mode = 0;
+    const int need = bk_shape_ok(Cin, Ce, Co, &p, &stream_mode);
     LP_CHECK_ARG(N > 0 && H > 0 && W > 0 && need > 0,
                  "lp_block_s1_f16: unsupported shape N=%d H=%d W=%d Cin=%d Ce=%d Co=%d (see lp_block_s1_supported)", N, H, W,
                  Cin, Ce, Co);
@@ -480,11 +565,17 @@ extern "C" int lp_block_s1_f16(const void* x, const void* w_exp_packed, const fl
         rc = make_tmap(&mwp, w_proj_packed, 2, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    cudaError_t e = cudaFuncSetAttribute((const void*)block_s1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(block_s1)");
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    cudaError_t le = launch_pdl(block_s1_kernel<0>, dim3(grid), dim3(BK_THREADS), (size_t)need, (cudaStream_t)stream, mx, mwe,
-                                mdw, mwp, p);
+    cudaError_t e, le;
+    if (stream_mode) {
+        e = cudaFuncSetAttribute((const void*)block_s1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(block_s1)");
+        le = launch_pdl(block_s1_kernel<1>, dim3(grid), dim3(BK_THREADS), (size_t)need, (cudaStream_t)stream, mx, mwe, mdw, mwp, p);
+    } else {
+        e = cudaFuncSetAttribute((const void*)block_s1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(block_s1)");
+        le = launch_pdl(block_s1_kernel<0>, dim3(grid), dim3(BK_THREADS), (size_t)need, (cudaStream_t)stream, mx, mwe, mdw, mwp, p);
+    }
     if (le != cudaSuccess) return cuda_fail(le, "launch block_s1_kernel");
     LP_LAUNCH_CHECK("block_s1_kernel");
     return LP_OK;

@@ -244,6 +244,9 @@ def test_head_fused(n, h, w, c1, c2, co, fp32):
     (1, 16, 16, 64, 160, 64, True),            # widest supported input / output
     # more tiles than SMs: several tiles per persistent CTA (X buffer hand-over, slot phases across tiles)
     (8, 128, 128, 16, 96, 16, True), (6, 80, 96, 32, 192, 32, True), (3, 112, 112, 24, 144, 24, True),
+    # streaming mode (weights through two-slot rings): stage-2-class blocks, odd and even slab counts, several tiles per CTA
+    (1, 32, 32, 48, 288, 48, True), (2, 16, 16, 48, 288, 48, False), (40, 32, 32, 48, 288, 48, True), (3, 96, 96, 48, 288, 48, True),
+    (2, 32, 32, 64, 384, 64, True), (1, 48, 48, 40, 320, 56, False),
 ])
 def test_block_s1_fused(n, h, w, cin, ce, co, res):
     """whole stride-1 InvBottleneck in one kernel (expand on tensor cores -> slab -> depthwise -> projection -> identity)
@@ -282,7 +285,7 @@ def test_block_s1_fused(n, h, w, cin, ce, co, res):
 
 def test_block_s1_unsupported_shapes():
     lib = _lib.load()
-    assert lib.lp_block_s1_supported(48, 288, 48) == 0      # shared-memory budget
+    assert lib.lp_block_s1_supported(72, 432, 72) == 0      # Cin > 64
     assert lib.lp_block_s1_supported(120, 720, 120) == 0    # Cin > 64
     x = torch.zeros(1, 16, 16, 120, dtype=torch.float16, device="cuda")
     rc = lib.lp_block_s1_f16(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), None, x.data_ptr(), None, 0, x.data_ptr(),
