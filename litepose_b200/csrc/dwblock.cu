@@ -349,7 +349,7 @@ block_s1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (!STREAM) mbar_wait(&bars->w_full, 0);           // depthwise weights resident
         pdl_wait();                                        // the identity rows are read from global memory
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
+            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y;
             if (grp && p.skew_ns) __nanosleep(p.skew_ns);
             // which of this thread's 4 expansion rows (haloed pixels) lie inside the image
             uint32_t inside = 0;

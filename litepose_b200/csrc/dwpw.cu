@@ -261,7 +261,6 @@ dw_project_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         };
         int it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
             for (int kb = 0; kb < p.nkb; ++kb, ++kbc) {
                 // (Splitting an odd last slab by rows between the two groups - each on its own M-tile, 2x4 micro-blocks -
                 // was measured in round 2: 12 % slower.  The FMA pipe, not the idle group, bounds the kernel, and the

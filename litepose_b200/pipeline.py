@@ -202,9 +202,6 @@ class LitePosePipeline(object):
                              "packed": [st["packed"], torch.zeros_like(st["packed"])], "gF": [None, None], "gP": [None, None],
                              "pstream": torch.cuda.Stream(device=self.device), "P_done": [None, None],
                              "consumer_done": [None, None], "idx": 0}
-        if st["graph"] is None and ov["gF"][0] is not None and st.get("ov_plant") is not plant:
-            ov["gF"] = [None, None]               # the plant hook changed: re-capture the forward graphs
-        st["ov_plant"] = plant
         b = ov["idx"]
         ov["idx"] = b ^ 1
         main = torch.cuda.current_stream()
