@@ -6,11 +6,13 @@
 //   warp 16 (1 thread) TMA producer: haloed 22x22x32-channel input slabs (hardware zero fill = conv padding) into a
 //                      4-deep ring, projection-weight K blocks into a 2-deep ring
 //   warps 0-15         depthwise on the CUDA cores, two groups of 8 warps working on the two 32-channel halves of a
-//                      64-channel K block: one 4x4 micro-block x channel pair per thread per slab (same
-//                      mixed-precision FHFMA inner loop and mirrored conflict-free LDS as dwconv.cu), results written
-//                      as fp16 straight into the 128B-swizzled K-major A-operand tiles in shared memory
+//                      64-channel K block: one 4x4 micro-block x channel pair per thread per slab; blocks (HEAD = 0):
+//                      packed fp16 HFMA2 in chains of two kernel rows folded into a running fp16 total, heads
+//                      (HEAD = 1): mixed-precision FHFMA with fp32 accumulation; mirrored conflict-free LDS as in
+//                      dwconv.cu; results written as fp16 straight into the 128B-swizzled K-major A-operand tiles
 //   warp 17 (1 thread) tcgen05.mma: D[256 px x Co] += A[256 x 64 ch] * Wp^T per 64-channel K block, fp32 in TMEM
 //   warps 0-15         epilogue: tcgen05.ld, + folded-BN bias (+ residual row), fp16, 16-byte stores of whole rows
+//                      (heads: deferred by one tile over two accumulator buffers, NCHW fp32/fp16 planes)
 // HBM traffic per block: read N*H*W*Ce*2 (+ N*H*W*Co*2 residual), write N*H*W*Co*2  -- the depthwise output
 // (N*H*W*Ce*2 written + read again) is gone; the kernel is bound by the FMA pipe (2*49 flop per expanded element).
 #include "common.cuh"
