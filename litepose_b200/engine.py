@@ -242,7 +242,8 @@ class LitePoseEngine(object):
         self.P = P
 
     # ------------------------------------------------------------------ plan
-    def _build_plan(self, n, h, w, in_dtype, out_fp32):
+    def _build_plan(self, n, h, w, in_dtype, out_fp32, pair=False):
+        """pair: the flip test as ONE batch of 2n (images n.. are the mirrored copies, produced by the fused stem)."""
         if h % 16 or w % 16:
             raise ValueError("LitePose input height/width must be multiples of 16, got %dx%d" % (h, w))
         lib, P, dev = self.lib, self.P, self.device
@@ -253,6 +254,11 @@ class LitePoseEngine(object):
             return torch.empty(shape, dtype=f16, device=dev)
 
         plan = {"in_ptr": ctypes.c_void_p(0), "flip": ctypes.c_int(0)}
+        n_in = n
+        if pair:
+            if not (self.fuse_stem and lib.lp_stem_fused_supported(h, w, P["stem_pw"]["N"])):
+                raise ValueError("pair-batch mode needs the fused stem (H even, W % 4 == 0)")
+            n = 2 * n
         h2, w2 = h // 2, w // 2
         x0 = buf(n, h2, w2, P["stem_pw"]["N"])
         st, d, q = P["stem"], P["stem_dw"], P["stem_pw"]
@@ -262,7 +268,7 @@ class LitePoseEngine(object):
             ops.append(_Op("stem_fused", lib.lp_stem_fused_f16,
                            [plan["in_ptr"], 1 if in_dtype == torch.float32 else 0, plan["flip"], st["w1p"].data_ptr(),
                             st["b"].data_ptr(), d["w"].data_ptr(), d["b"].data_ptr(), q["w"].data_ptr(), q["b"].data_ptr(),
-                            x0.data_ptr(), n, h, w, q["N"]]))
+                            x0.data_ptr(), n_in, h, w, q["N"]]))
         else:
             a0 = buf(n, h2, w2, 32)
             a1 = buf(n, h2, w2, 32)
@@ -359,10 +365,10 @@ class LitePoseEngine(object):
 
     def plan_for(self, n, h, w, in_dtype, out_fp32, flip=False):
         # the flip pass owns its own buffers so that both passes can be in flight at once
-        key = (n, h, w, in_dtype, out_fp32, bool(flip))
+        key = (n, h, w, in_dtype, out_fp32, flip if flip == "both" else bool(flip))
         pl = self.plans.get(key)
         if pl is None:
-            pl = self._build_plan(n, h, w, in_dtype, out_fp32)
+            pl = self._build_plan(n, h, w, in_dtype, out_fp32, pair=(flip == "both"))
             self.plans[key] = pl
         return pl
 
@@ -375,7 +381,8 @@ class LitePoseEngine(object):
 
     def run(self, x, flip=False, out_fp32=True, clone=True):
         """x: NCHW fp16/fp32 CUDA tensor.  Returns [out0 [N,2J,H/4,W/4], out1 [N,J,H/2,W/2]]
-        (fp32 when out_fp32 else fp16).  ``flip`` computes the forward of torch.flip(x,[3])."""
+        (fp32 when out_fp32 else fp16).  ``flip`` computes the forward of torch.flip(x,[3]); ``flip="both"`` runs the flip test
+        as ONE batch of 2N (outputs [2N, ...]: rows N.. belong to the mirrored images)."""
         if self.device.type != "cuda":
             raise RuntimeError("LitePoseEngine.run needs a CUDA device (this engine was prepared on %s)" % self.device)
         assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
@@ -396,7 +403,7 @@ class LitePoseEngine(object):
                 plan["static_in"].copy_(x)
                 if key not in g:
                     plan["in_ptr"].value = plan["static_in"].data_ptr()
-                    plan["flip"].value = 1 if flip else 0
+                    plan["flip"].value = 2 if flip == "both" else (1 if flip else 0)
                     self._launch_all(plan, stream)      # warm-up (also sets func attributes)
                     torch.cuda.current_stream().synchronize()
                     cg = torch.cuda.CUDAGraph()
@@ -406,7 +413,7 @@ class LitePoseEngine(object):
                 g[key].replay()
             else:
                 plan["in_ptr"].value = x.data_ptr()
-                plan["flip"].value = 1 if flip else 0
+                plan["flip"].value = 2 if flip == "both" else (1 if flip else 0)
                 self._launch_all(plan, stream)
         outs = plan["outs"]
         return [o.clone() for o in outs] if clone else list(outs)

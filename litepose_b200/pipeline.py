@@ -90,6 +90,7 @@ class LitePosePipeline(object):
         self.use_graphs = use_graphs
         import os
         self.two_streams = os.environ.get("LP_TWO_STREAMS", "1") != "0"
+        self.pair_batch = os.environ.get("LP_PAIR_BATCH", "0") == "1"      # experiment: both passes as one batch of 2N
         # persons per image in the fixed-size packed payload (the D2H copy / NCCL gather of every step).  The reference
         # returns every person it finds (lib/core/group.py:96,269-291); an image with more than ``keep`` persons is
         # never clipped: step() fetches the full result from the parser's buffers (capacity J*K persons) in a second
@@ -142,7 +143,13 @@ class LitePosePipeline(object):
     def _forward_part(self, st, x, det, tag):
         """Both network passes + fused glue (+ the benchmark's planted persons) -> det / tag of this step."""
         eng, J = self.engine, self.params.num_joints
-        if self.flip and self.two_streams:
+        if self.flip and self.pair_batch:
+            # the flip test as ONE batch of 2N: half the launches, twice the tiles per persistent kernel
+            both = eng.run(x, flip="both", out_fp32=True, clone=False)
+            nb = x.shape[0]
+            o = [both[0][:nb], both[1][:nb]]
+            f = [both[0][nb:], both[1][nb:]]
+        elif self.flip and self.two_streams:
             # the plain and the mirrored pass are independent until the glue: fork onto a side stream so that one pass'
             # kernels fill the launch gaps and tails of the other (each pass has its own plan buffers)
             main = torch.cuda.current_stream()
