@@ -159,3 +159,36 @@ def test_folded_checkpoint_roundtrip(tmp_path):
     assert back.channels == eng.channels and back.arch == arch
     with pytest.raises(RuntimeError):
         back.run(torch.zeros(1, 3, 64, 64))
+
+
+def test_block_and_stem_host_helpers():
+    """host-only entry points of the round-2 kernels (no GPU needed): shape admission and weight packing"""
+    import numpy as np
+    from litepose_b200 import _lib
+    lib = _lib.load()
+    # LitePose-S: stages 0-2 fit the block kernel (stage 2 in streaming mode), stage 3 (Cin = 120) does not
+    assert [lib.lp_block_s1_supported(*c) for c in ((16, 96, 16), (32, 192, 32), (48, 288, 48), (120, 720, 120), (48, 288, 120))] \
+        == [1, 1, 1, 0, 0]
+    assert lib.lp_block_s1_supported(12, 72, 16) == 0 and lib.lp_block_s1_supported(16, 96, 20) == 0     # multiples of 8
+    assert lib.lp_stem_fused_supported(512, 512, 16) == 1 and lib.lp_stem_fused_supported(512, 510, 16) == 0
+    assert lib.lp_stem_fused_supported(640, 640, 24) == 1 and lib.lp_stem_fused_supported(64, 64, 40) == 0
+    cin, ce = 24, 80
+    w = (np.arange(ce * cin, dtype=np.uint16).reshape(ce, cin) + 1)
+    out = np.full(lib.lp_block_s1_wexp_elems(cin, ce), 0xffff, np.uint16)
+    assert out.size == 96 * 64                      # 3 slabs of 32 rows, K padded to 64
+    _lib.check(lib.lp_block_s1_pack_wexp(w.ctypes.data, cin, ce, out.ctypes.data))
+    out = out.reshape(96, 64)
+    assert np.array_equal(out[:ce, :cin], w) and not out[:ce, cin:].any() and not out[ce:].any()
+
+
+def test_dropin_install_refuses_late_binding(tmp_path):
+    """litepose_b200.dropin.install() must raise when a reference package of the same name is already imported"""
+    import subprocess
+    import sys
+    pkg = tmp_path / "models"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("x = 1\n")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import models; import litepose_b200.dropin as d\n"
+            "try:\n    d.install()\nexcept ImportError as e:\n    print('refused', 'models' in str(e))\n" % (ROOT, str(tmp_path)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "refused True" in r.stdout, r.stdout + r.stderr
