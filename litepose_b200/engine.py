@@ -363,9 +363,11 @@ class LitePoseEngine(object):
         plan.update({"ops": ops, "outs": outs, "keep": keep, "graph": None, "static_in": None})
         return plan
 
-    def plan_for(self, n, h, w, in_dtype, out_fp32, flip=False):
-        # the flip pass owns its own buffers so that both passes can be in flight at once
-        key = (n, h, w, in_dtype, out_fp32, flip if flip == "both" else bool(flip))
+    def plan_for(self, n, h, w, in_dtype, out_fp32, flip=False, slot=0):
+        # the flip pass owns its own buffers so that both passes can be in flight at once; ``slot`` selects one of
+        # several buffer sets (the pipeline alternates two so that step i+1's passes never touch the outputs step i's
+        # glue is still reading)
+        key = (n, h, w, in_dtype, out_fp32, flip if flip == "both" else bool(flip), slot)
         pl = self.plans.get(key)
         if pl is None:
             pl = self._build_plan(n, h, w, in_dtype, out_fp32, pair=(flip == "both"))
@@ -379,7 +381,7 @@ class LitePoseEngine(object):
             if rc:
                 _lib.check(rc, op.name)
 
-    def run(self, x, flip=False, out_fp32=True, clone=True):
+    def run(self, x, flip=False, out_fp32=True, clone=True, slot=0):
         """x: NCHW fp16/fp32 CUDA tensor.  Returns [out0 [N,2J,H/4,W/4], out1 [N,J,H/2,W/2]]
         (fp32 when out_fp32 else fp16).  ``flip`` computes the forward of torch.flip(x,[3]); ``flip="both"`` runs the flip test
         as ONE batch of 2N (outputs [2N, ...]: rows N.. belong to the mirrored images)."""
@@ -390,7 +392,7 @@ class LitePoseEngine(object):
             x = x.float()
         x = x.contiguous()
         n, _, h, w = x.shape
-        plan = self.plan_for(n, h, w, x.dtype, out_fp32, flip)
+        plan = self.plan_for(n, h, w, x.dtype, out_fp32, flip, slot)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             if self.use_graphs:
