@@ -143,8 +143,10 @@ class LitePose(nn.Module):
     # -- engine management -------------------------------------------------
     def lp_invalidate(self):
         """Drop the packed-weight cache.  Not needed after the usual mutations: .to()/.half(), load_state_dict,
-        train()/eval() switches and any in-place update of a parameter or buffer (optimizer step, BN statistics,
-        ``p.data.copy_``) are detected; call it after replacing ``p.data`` with a new tensor of version 0."""
+        train()/eval() switches, re-assignment, and any in-place update of a parameter or buffer itself (optimizer
+        step, BN statistics, ``p.copy_`` / ``p.mul_`` under no_grad) are detected.  NOT detected: writes through a
+        detached alias (``p.data.copy_(...)``, ``p.detach().mul_()``: the alias carries its own version counter) -
+        call this after those."""
         self._lp_cache.clear()
 
     def _apply(self, fn, *args, **kwargs):      # .cuda() / .half() / .float() / .to()
@@ -166,14 +168,11 @@ class LitePose(nn.Module):
         return super().train(mode)
 
     def _lp_signature(self):
-        """Sum of the autograd version counters + identities of all parameters and buffers: changes with every
-        in-place update (optimizer.step, running statistics, .data.copy_/.mul_) and with every re-assignment."""
-        sig = 0
-        for t in self.parameters():
-            sig += t._version + (id(t) & 0xffff)
-        for t in self.buffers():
-            sig += t._version + (id(t) & 0xffff)
-        return sig
+        """Hash over (identity, data pointer, autograd version counter) of every parameter and buffer: changes with
+        every in-place update of the tensor itself (optimizer.step, running statistics, copy_/mul_ under no_grad) and with
+        every re-assignment; writes through ``.data`` / ``.detach()`` aliases are invisible to it (lp_invalidate)."""
+        return hash(tuple((id(t), t.data_ptr(), t._version)
+                          for group in (self.parameters(), self.buffers()) for t in group))
 
     def _replicate_for_data_parallel(self):
         # nn.DataParallel replicates the master on every forward: publish the master's signature so that the replicas

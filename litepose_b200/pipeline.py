@@ -298,6 +298,13 @@ class LitePosePipeline(object):
         [N, keep*J*(3+T) + keep + 1] (keypoints, scores, person count)."""
         n, _, s_h, s_w = x_dev.shape
         st = self._get_state(n, s_h, s_w, x_dev.dtype, plant)
+        ov = st.get("ov")
+        if ov is not None:
+            # det / tag / packed are shared with buffer set 0 of the overlapped form: an overlapped step that is still
+            # running on the parser stream must finish before this stream overwrites them
+            for ev in ov["P_done"]:
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
         if not self.use_graphs:
             return self._device_step(st, x_dev)
         st["x"].copy_(x_dev, non_blocking=True)
@@ -336,6 +343,9 @@ class LitePosePipeline(object):
         main = torch.cuda.current_stream()
         a = self._async
         if a is None or a["key"] != (n, s_h, s_w, frames_pinned.dtype, id(group)):
+            if a is not None and any(sl["busy"] for sl in a["slots"]):
+                raise RuntimeError("LitePosePipeline.submit: collect() the outstanding tickets before changing the batch "
+                                   "shape, dtype or group")
             world = dist.get_world_size(group) if group is not None else 1
             rank = dist.get_rank(group) if group is not None else 0
             st = self._get_state(n, s_h, s_w, frames_pinned.dtype, plant)

@@ -81,6 +81,38 @@ def test_dropin_module_contract():
     assert next(half.parameters()).dtype == torch.float16
 
 
+def test_engine_cache_signature_tracks_weight_updates():
+    """The packed-weight cache key (stale engine after in-place updates) changes with every in-place
+    update, re-assignment and load, and with nothing else."""
+    from litepose_b200.lib.models.pose_mobilenet import get_pose_net
+    model = get_pose_net(get_cfg(input_size=64), False, get_arch("XS")).eval()
+    s0 = model._lp_signature()
+    assert model._lp_signature() == s0
+    with torch.no_grad():
+        model(synth.make_frames(1, 64, seed=1))          # an eval forward touches nothing
+    assert model._lp_signature() == s0
+    with torch.no_grad():
+        model.first[0][0].weight.mul_(1.5)               # optimizer-style in-place update
+    s1 = model._lp_signature()
+    assert s1 != s0
+    model.first[3].running_mean.add_(0.1)                # BN statistics
+    s2 = model._lp_signature()
+    assert s2 != s1
+    model.first[2].weight = torch.nn.Parameter(model.first[2].weight.detach().clone())   # re-assignment
+    assert model._lp_signature() != s2
+    sd = copy.deepcopy(model.state_dict())
+    s3 = model._lp_signature()
+    model.load_state_dict(sd)
+    assert model._lp_signature() != s3
+    assert copy.deepcopy(model)._lp_cache is not model._lp_cache
+    # writes through ``.data`` have their own version counter: documented as needing lp_invalidate()
+    s4 = model._lp_signature()
+    model.first[3].running_mean.data.add_(0.1)
+    assert model._lp_signature() == s4
+    model.lp_invalidate()
+    assert not model._lp_cache.engines
+
+
 def test_shard_range():
     assert [shard_range(256, r, 8) for r in range(8)] == [(32 * r, 32 * r + 32) for r in range(8)]
     parts = [shard_range(10, r, 4) for r in range(4)]
