@@ -186,7 +186,8 @@ int lp_nms_topk_f32(const float* det, const float* tag, int N, int J, int H, int
  * person-creation order; num_people [N] i32 (true count, may exceed pcap ->
  * LP_ERR_CAPACITY is NOT raised on the device; the caller compares against pcap;
  * pcap = J*K can never overflow).  Thresholds are doubles because the reference
- * compares float64 joint rows against Python floats (group.py:38-41,84). */
+ * compares float64 joint rows against Python floats (group.py:38-41,84).
+ * K, max_num_people <= 64 (one cost-matrix column per lane up to 32, two above). */
 size_t lp_tag_match_workspace_bytes(int N, int J, int K, int T, int pcap);
 int lp_tag_match_f32(const float* val_k, const int32_t* ind_k, const float* tag_k, int N, int J,
                      int K, int T, int W, const int32_t* joint_order, double det_threshold,
@@ -257,6 +258,38 @@ int lp_assign_f32(const int32_t* count, const float* val, const float* tag, cons
 int lp_glue_f32(const float* o0, const float* o1, const float* f0, const float* f1,
                 const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd, int Wd,
                 float* det, float* tag, lp_stream_t stream);
+
+/* Multi-scale test (TEST.SCALE_FACTOR with more than one entry; reference valid.py:205-225 +
+ * aggregate_results lib/core/inference.py:176-208): ONE call per scale, largest scale first, on
+ * that scale's network outputs (h, w follow the scale; Hd, Wd are the common size: base_size
+ * with PROJECT2IMAGE, else the size of the first scale's heat-maps).  The scale's flip-averaged
+ * heat-map, resampled to (Hd,Wd), is stored (accumulate == 0: first scale) or added to det
+ * (`final_heatmaps += ...`); divide_by != 1 divides the sum afterwards
+ * (`final_heatmaps / len(SCALE_FACTOR)`, valid.py:223: pass it with the last scale).  tag is
+ * written (resampled to (Hd,Wd)) only for the scale == 1 call; pass NULL for the other scales
+ * (inference.py:179-190).  Projection ratios down to a 4.6x shrink are supported. */
+int lp_glue_scale_f32(const float* o0, const float* o1, const float* f0, const float* f1,
+                      const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd,
+                      int Wd, int accumulate, float divide_by, float* det, float* tag,
+                      lp_stream_t stream);
+
+/* ---- per-step host payload ------------------------------------------------------
+ * What HeatmapParser.parse hands back to valid.py:227 (lib/core/group.py:269-291), for a whole
+ * batch, as one fixed-size row per image that a single D2H copy / NCCL gather carries:
+ *   packed [N, keep*row + keep + 1] f32 = keep persons x row (= J*(3+T)) keypoint floats |
+ *   keep scores | person count.  ans [N,pcap,J,3+T], scores [N,pcap], num_people [N] are the
+ * parser's result buffers; keep <= pcap.  The count is the TRUE count (it may exceed keep: the
+ * caller then fetches the image from the parser's buffers - nothing is clipped silently). */
+int lp_pack_payload_f32(const float* ans, const int32_t* num_people, const float* scores, int N,
+                        int pcap, int row, int keep, float* packed, lp_stream_t stream);
+
+/* ---- synthetic workload: planted persons (bench / tests only) --------------------
+ * A random-weight network detects nobody, so the benchmark plants persons between glue and
+ * parser: det[det_index[i]] = max(det[..], det_value[i]) (atomic, order independent) and
+ * tag[tag_index[i]] = tag_value[i] (indices unique).  Flat element indices, int64 device. */
+int lp_plant_crowd_f32(float* det, const int64_t* det_index, const float* det_value,
+                       int64_t n_det, float* tag, const int64_t* tag_index,
+                       const float* tag_value, int64_t n_tag, lp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@
 
 namespace lp {
 
-constexpr int GL_TO = 64;          // output tile side
+constexpr int GL_TO = 64;          // output tile side (halved by the host until the mid-level footprint fits GL_TM)
 constexpr int GL_TM = 40;          // max mid-level tile side kept in shared memory
 constexpr int GL_THREADS = 256;
 
@@ -41,7 +41,8 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ p, int W, cons
 __global__ void __launch_bounds__(GL_THREADS)
 glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const float* __restrict__ f0,
             const float* __restrict__ f1, const int32_t* __restrict__ flip_index, int J, int h, int w, int flip, int Hd,
-            int Wd, int tiles_x, float* __restrict__ det, float* __restrict__ tag) {
+            int Wd, int tiles_x, int to, int accumulate, float divide_by, float* __restrict__ det,
+            float* __restrict__ tag) {
     __shared__ float s_ha[GL_TM][GL_TM + 1], s_hf[GL_TM][GL_TM + 1], s_t0[GL_TM][GL_TM + 1], s_t1[GL_TM][GL_TM + 1];
     const int n = blockIdx.z, j = blockIdx.y;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -49,8 +50,8 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
     const int T = flip ? 2 : 1;
     const bool project = !(Hd == H2 && Wd == W2);
     const float sy = (float)H2 / (float)Hd, sx = (float)W2 / (float)Wd;
-    const int oy0 = ty * GL_TO, ox0 = tx * GL_TO;
-    const int oy1 = min(oy0 + GL_TO, Hd) - 1, ox1 = min(ox0 + GL_TO, Wd) - 1;
+    const int oy0 = ty * to, ox0 = tx * to;
+    const int oy1 = min(oy0 + to, Hd) - 1, ox1 = min(ox0 + to, Wd) - 1;
     // mid-level footprint of this output tile
     int my0, my1, mx0, mx1;
     if (project) {
@@ -59,7 +60,7 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
     } else {
         my0 = oy0; my1 = oy1; mx0 = ox0; mx1 = ox1;
     }
-    const int mh = my1 - my0 + 1, mw = mx1 - mx0 + 1;   // <= GL_TM guaranteed by the host (scale <= 0.6) unless !project
+    const int mh = my1 - my0 + 1, mw = mx1 - mx0 + 1;   // <= GL_TM guaranteed by the host (choice of `to`) unless !project
     const float us_y = (float)h / (float)H2, us_x = (float)w / (float)W2;   // 0.5
 
     const size_t hw = (size_t)h * w, HW2 = (size_t)H2 * W2;
@@ -95,7 +96,10 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
     float* tplane = tag + ((size_t)n * J + j) * Hd * Wd * T;
     const int th = oy1 - oy0 + 1, tw = ox1 - ox0 + 1;
 
-    if (project && Hd == 2 * H2 && Wd == 2 * W2 && flip) {
+    // multi-scale aggregation (inference.py:176-208): det accumulates over the scales, the division by the number of
+    // scales (valid.py:223) rides on the last call; scales other than 1 write no tags (tag == nullptr)
+    const bool plain = !accumulate && divide_by == 1.f && tag != nullptr;
+    if (project && Hd == 2 * H2 && Wd == 2 * W2 && flip && plain) {
         // exact x2 projection (the evaluation config): out[2m] = .25 s[m-1] + .75 s[m], out[2m+1] = .75 s[m] + .25 s[m+1]
         // (edge-clamped).  One thread produces a 2x2 output quad from a 3x3 mid-level neighbourhood: 9 LDS per map
         // instead of 16, constant weights, 16-byte tag stores.
@@ -158,12 +162,13 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
             }
         }
         const size_t o = (size_t)Y * Wd + X;
-        if (flip) {
-            dplane[o] = (ha + hf) / 2.f;
-            *reinterpret_cast<float2*>(tplane + o * 2) = make_float2(t0, t1);
-        } else {
-            dplane[o] = ha;
-            tplane[o] = t0;
+        float v = flip ? (ha + hf) / 2.f : ha;
+        if (accumulate) v = dplane[o] + v;
+        if (divide_by != 1.f) v = v / divide_by;
+        dplane[o] = v;
+        if (tag != nullptr) {
+            if (flip) *reinterpret_cast<float2*>(tplane + o * 2) = make_float2(t0, t1);
+            else tplane[o] = t0;
         }
     }
 }
@@ -290,33 +295,57 @@ glue_x4_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const
 
 using namespace lp;
 
-extern "C" int lp_glue_f32(const float* o0, const float* o1, const float* f0, const float* f1, const int32_t* flip_index,
-                           int N, int J, int h, int w, int flip, int Hd, int Wd, float* det, float* tag,
-                           lp_stream_t stream) {
-    LP_CHECK_ARG(o0 && o1 && det && tag, "lp_glue_f32: null pointer");
-    LP_CHECK_ARG(!flip || (f0 && f1 && flip_index), "lp_glue_f32: flip pass needs f0, f1, flip_index");
+// picks the output tile side so that the mid-level footprint of a tile fits the shared tile; 0 = ratio not supported
+static int glue_tile_side(int h, int w, int Hd, int Wd) {
+    for (int to = GL_TO; to >= 8; to >>= 1)
+        if ((double)(2 * h) / Hd * to + 3 <= GL_TM && (double)(2 * w) / Wd * to + 3 <= GL_TM) return to;
+    return 0;
+}
+
+static int glue_launch(const char* who, const float* o0, const float* o1, const float* f0, const float* f1,
+                       const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd, int Wd, int accumulate,
+                       float divide_by, float* det, float* tag, bool allow_x4, lp_stream_t stream) {
+    LP_CHECK_ARG(o0 && o1 && det, "%s: null pointer", who);
+    LP_CHECK_ARG(!flip || (f0 && f1 && flip_index), "%s: flip pass needs f0, f1, flip_index", who);
     LP_CHECK_ARG(N > 0 && N <= 65535 && J > 0 && J <= 65535 && h > 0 && w > 0 && Hd > 0 && Wd > 0,
-                 "lp_glue_f32: bad shape N=%d J=%d h=%d w=%d Hd=%d Wd=%d", N, J, h, w, Hd, Wd);
+                 "%s: bad shape N=%d J=%d h=%d w=%d Hd=%d Wd=%d", who, N, J, h, w, Hd, Wd);
+    LP_CHECK_ARG(divide_by > 0.f, "%s: divide_by must be > 0", who);
     const bool project = !(Hd == 2 * h && Wd == 2 * w);
+    int to = GL_TO;
     if (project) {
-        // the shared mid-level tile must cover the footprint of a 64x64 output tile
-        LP_CHECK_ARG((double)(2 * h) / Hd * GL_TO + 3 <= GL_TM && (double)(2 * w) / Wd * GL_TO + 3 <= GL_TM,
-                     "lp_glue_f32: projection must up-sample by >= 1.73x (got %dx%d -> %dx%d)", 2 * h, 2 * w, Hd, Wd);
+        // the shared mid-level tile must cover the footprint of one output tile
+        to = glue_tile_side(h, w, Hd, Wd);
+        LP_CHECK_ARG(to > 0, "%s: projection %dx%d -> %dx%d shrinks by more than 4.6x (not supported)", who, 2 * h, 2 * w,
+                     Hd, Wd);
     }
-    if (((reinterpret_cast<uintptr_t>(tag) & 15) || (reinterpret_cast<uintptr_t>(det) & 7)) && flip) {
-        set_error("lp_glue_f32: tag must be 16-byte and det 8-byte aligned");
+    if (flip && ((tag && (reinterpret_cast<uintptr_t>(tag) & 15)) || (reinterpret_cast<uintptr_t>(det) & 7))) {
+        set_error("%s: tag must be 16-byte and det 8-byte aligned", who);
         return LP_ERR_ALIGN;
     }
-    if (flip && Hd == 4 * h && Wd == 4 * w && (long long)N * J <= 65535 && h <= 65535) {
+    if (allow_x4 && flip && Hd == 4 * h && Wd == 4 * w && (long long)N * J <= 65535 && h <= 65535) {
         dim3 grid((w + 127) / 128, h, N * J);
         glue_x4_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(o0, o1, f0, f1, flip_index, J, h, w, det, tag);
         LP_LAUNCH_CHECK("glue_x4_kernel");
         return LP_OK;
     }
-    const int tiles_x = (Wd + GL_TO - 1) / GL_TO, tiles_y = (Hd + GL_TO - 1) / GL_TO;
+    const int tiles_x = (Wd + to - 1) / to, tiles_y = (Hd + to - 1) / to;
     dim3 grid(tiles_x * tiles_y, J, N);
     glue_kernel<<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(o0, o1, f0, f1, flip_index, J, h, w, flip, Hd, Wd, tiles_x,
-                                                             det, tag);
+                                                             to, accumulate, divide_by, det, tag);
     LP_LAUNCH_CHECK("glue_kernel");
     return LP_OK;
+}
+
+extern "C" int lp_glue_f32(const float* o0, const float* o1, const float* f0, const float* f1, const int32_t* flip_index,
+                           int N, int J, int h, int w, int flip, int Hd, int Wd, float* det, float* tag,
+                           lp_stream_t stream) {
+    LP_CHECK_ARG(tag, "lp_glue_f32: null pointer");
+    return glue_launch("lp_glue_f32", o0, o1, f0, f1, flip_index, N, J, h, w, flip, Hd, Wd, 0, 1.f, det, tag, true, stream);
+}
+
+extern "C" int lp_glue_scale_f32(const float* o0, const float* o1, const float* f0, const float* f1,
+                                 const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd, int Wd,
+                                 int accumulate, float divide_by, float* det, float* tag, lp_stream_t stream) {
+    return glue_launch("lp_glue_scale_f32", o0, o1, f0, f1, flip_index, N, J, h, w, flip, Hd, Wd, accumulate ? 1 : 0,
+                       divide_by, det, tag, !accumulate && divide_by == 1.f && tag != nullptr, stream);
 }

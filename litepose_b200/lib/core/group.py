@@ -33,19 +33,28 @@ class HeatmapParser(object):
     def __init__(self, cfg):
         self.params = Params(cfg)
         self.tag_per_joint = cfg.MODEL.TAG_PER_JOINT
-        if not self.tag_per_joint:
-            raise NotImplementedError("TAG_PER_JOINT=False is not supported by the device parser")
         p = self.params
         self.device_parser = DeviceParser(p.num_joints, p.max_num_people, p.detection_threshold, p.tag_threshold,
                                           p.use_detection_val, p.ignore_too_much, p.joint_order,
                                           cfg.TEST.NMS_KERNEL, cfg.TEST.NMS_PADDING)
 
+    def _tags(self, det, tag):
+        """[N,Jt,H,W(,T)] -> float32 [N,J,H,W,T].  MODEL.TAG_PER_JOINT=False: the network emits ONE tag map shared by all
+        joints; the reference expands it over the joints for the gather (group.py:150-152) and means to tile it for
+        refine (group.py:283-286 - where its own code stops on an unassigned name as soon as a person is found, so
+        that branch of the reference returns nothing to compare with: the tiled maps are what it was written to use)."""
+        if tag.dim() == 4:
+            tag = tag.unsqueeze(4)
+        if not self.tag_per_joint:
+            if tag.shape[1] != 1:
+                raise ValueError("TAG_PER_JOINT=False expects one tag map per image (got %d)" % tag.shape[1])
+            tag = tag.expand(-1, det.shape[1], -1, -1, -1)
+        return tag.float().contiguous()
+
     # -- reference sub-methods (public names kept; no external callers in the reference)
     def top_k(self, det, tag):
         """group.py:141-176 -> dict of numpy arrays (canonical tie order, see include/litepose_b200.h)."""
-        if tag.dim() == 4:
-            tag = tag.unsqueeze(4)
-        val_k, ind_k, tag_k = self.device_parser.top_k_device(det.float(), tag.float())
+        val_k, ind_k, tag_k = self.device_parser.top_k_device(det.float(), self._tags(det, tag))
         w = det.shape[3]
         ind = ind_k.cpu().numpy().astype(np.int64)
         return {"tag_k": tag_k.cpu().numpy(), "loc_k": np.stack((ind % w, ind // w), axis=3),
@@ -54,7 +63,7 @@ class HeatmapParser(object):
     def parse_batch(self, det, tag, adjust=True, refine=True):
         """N images -> list of N (ans, scores) pairs, each exactly what the reference's
         ``parse(det[i:i+1], tag[i:i+1])`` returns."""
-        res = self.device_parser.run(det.float(), tag.float(), adjust, refine)
+        res = self.device_parser.run(det.float(), self._tags(det, tag), adjust, refine)
         return [([a], s) for a, s in DeviceParser.to_reference(*res)]
 
     def parse(self, det, tag, adjust=True, refine=True):

@@ -19,8 +19,8 @@ class DeviceParser(object):
                              % (nms_kernel, nms_padding))
         if detection_threshold < 0:
             raise ValueError("DETECTION_THRESHOLD must be >= 0 (slots with val <= 0 are canonicalised)")
-        if max_num_people > 32:
-            raise ValueError("MAX_NUM_PEOPLE > 32 is not supported by the warp-wide matcher")
+        if max_num_people > 64:
+            raise ValueError("MAX_NUM_PEOPLE > 64 is not supported by the warp-wide matcher (two columns per lane)")
         self.lib = _lib.load()
         self.J = int(num_joints)
         self.K = int(max_num_people)

@@ -23,8 +23,9 @@ from .parser import DeviceParser
 class PlantedCrowd(object):
     """Sparse planted persons for the synthetic benchmark: Gaussian det patches are
     max-composited into the heat-maps and 9x9 tag patches overwrite the tag maps (all T).
-    Index/value tensors are built once on the host (litepose_b200.synth conventions) and
-    applied with three small torch index ops on the device."""
+    Index/value lists are built once on the host (litepose_b200.synth conventions) and applied by ONE kernel of the
+    library on the device (lp_plant_crowd_f32); host tensors (the CPU baseline arm, the oracle side of the tests) take
+    the equivalent torch index ops."""
 
     def __init__(self, n, num_joints, h, w, t, num_people=5, seed=0, device="cuda", presence=0.9, sigma=2.0):
         import numpy as np
@@ -54,18 +55,33 @@ class PlantedCrowd(object):
                     tv = (2.0 * p + rng.randn(81, t) * 0.05).astype(np.float32)
                     tidx.append((flat[:, None] * t + np.arange(t)[None, :]).ravel())
                     tval.append(tv.ravel())
-        cat = lambda l, dt: torch.from_numpy(np.concatenate(l).astype(dt)) if l else torch.zeros(0, dtype=torch.int64)
-        self.didx = cat(didx, np.int64).to(device)
-        self.dval = cat(dval, np.float32).to(device) if didx else torch.zeros(0, device=device)
-        self.tidx = cat(tidx, np.int64).to(device)
-        self.tval = cat(tval, np.float32).to(device) if tidx else torch.zeros(0, device=device)
+        if didx:
+            di, dv = np.concatenate(didx).astype(np.int64), np.concatenate(dval).astype(np.float32)
+            ti, tv = np.concatenate(tidx).astype(np.int64), np.concatenate(tval).astype(np.float32)
+            # overlapping tag patches: the LAST writer wins (what a sequential index_copy_ does); de-duplicated here so
+            # that the device kernel's plain stores are race free and every device sees the same maps
+            _, first_rev = np.unique(ti[::-1], return_index=True)
+            last = np.sort(ti.size - 1 - first_rev)
+            ti, tv = ti[last], tv[last]
+        else:
+            di = ti = np.zeros(0, np.int64)
+            dv = tv = np.zeros(0, np.float32)
+        self.didx, self.dval = torch.from_numpy(di).to(device), torch.from_numpy(dv).to(device)
+        self.tidx, self.tval = torch.from_numpy(ti).to(device), torch.from_numpy(tv).to(device)
 
     def apply(self, det, tag):
-        if self.didx.numel():
-            d = det.view(-1)
-            # overlapping patches: scatter-max keeps the larger amplitude, order independent
-            d.scatter_reduce_(0, self.didx, self.dval, reduce="amax", include_self=True)
-            tag.view(-1).index_copy_(0, self.tidx, self.tval)
+        if not self.didx.numel():
+            return det, tag
+        if det.is_cuda:
+            # one launch of the library's kernel (overlapping det patches: atomic max, order independent)
+            _lib.check(_lib.load().lp_plant_crowd_f32(det.data_ptr(), self.didx.data_ptr(), self.dval.data_ptr(),
+                                                      self.didx.numel(), tag.data_ptr(), self.tidx.data_ptr(),
+                                                      self.tval.data_ptr(), self.tidx.numel(),
+                                                      torch.cuda.current_stream().cuda_stream), "lp_plant_crowd_f32")
+            return det, tag
+        # host tensors: the same workload for the CPU baseline arm and the oracle side of the tests
+        det.view(-1).scatter_reduce_(0, self.didx, self.dval, reduce="amax", include_self=True)
+        tag.view(-1).index_copy_(0, self.tidx, self.tval)
         return det, tag
 
 
@@ -84,6 +100,7 @@ class LitePosePipeline(object):
                                    p.use_detection_val, p.ignore_too_much, p.joint_order, cfg.TEST.NMS_KERNEL,
                                    cfg.TEST.NMS_PADDING)
         self.flip = bool(cfg.TEST.FLIP_TEST)
+        self.scales = sorted((float(v) for v in cfg.TEST.SCALE_FACTOR), reverse=True)    # valid.py:205: largest first
         self.project = bool(cfg.TEST.PROJECT2IMAGE)
         self.adjust, self.refine = bool(cfg.TEST.ADJUST), bool(cfg.TEST.REFINE)
         self.fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device=self.device)
@@ -108,8 +125,11 @@ class LitePosePipeline(object):
         def bad(what):
             raise NotImplementedError("LitePosePipeline: %s is not supported by the fused glue kernel "
                                       "(use the reference's core.inference on the drop-in module instead)" % what)
-        if [float(v) for v in cfg.TEST.SCALE_FACTOR] != [1.0]:
-            bad("multi-scale test (TEST.SCALE_FACTOR=%r)" % (list(cfg.TEST.SCALE_FACTOR),))
+        scales = [float(v) for v in cfg.TEST.SCALE_FACTOR]
+        if len(scales) != len(set(scales)) or 1.0 not in scales or min(scales) <= 0:
+            # the reference takes the tags from the scale-1 pass only (inference.py:179-190): without it torch.cat of an
+            # empty list fails at valid.py:224
+            raise ValueError("TEST.SCALE_FACTOR=%r: distinct positive scales including 1 expected" % (scales,))
         if cfg.DATASET.WITH_CENTER:
             bad("DATASET.WITH_CENTER")
         if not cfg.MODEL.TAG_PER_JOINT:
@@ -193,10 +213,9 @@ class LitePosePipeline(object):
                                                        ans.shape[1], ans.shape[2], ans.shape[3],
                                                        torch.cuda.current_stream().cuda_stream), "lp_transform_preds_f32")
         st["full"] = (ans, num, scores)       # parser-owned buffers (capacity J*K persons), valid until the next step
-        k = self.keep
-        packed[:, :k * st["row"]].copy_(ans[:, :k].reshape(n, -1))
-        packed[:, k * st["row"]:k * st["row"] + k].copy_(scores[:, :k])
-        packed[:, -1].copy_(num.float())
+        _lib.check(self.lib.lp_pack_payload_f32(ans.data_ptr(), num.data_ptr(), scores.data_ptr(), n, ans.shape[1],
+                                                st["row"], self.keep, packed.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "lp_pack_payload_f32")
         return packed
 
     # -- device step (everything between the H2D copy and the D2H copy) -------------
@@ -258,13 +277,16 @@ class LitePosePipeline(object):
         st["ov_last"] = b
         return ov["packed"][b], ev
 
-    def _get_state(self, n, s_h, s_w, dtype, plant):
-        key = (n, s_h, s_w, dtype, self._final is not None)
+    def _get_state(self, n, s_h, s_w, dtype, plant, det_hw=None):
+        if len(self.scales) > 1 and det_hw is None:
+            raise RuntimeError("TEST.SCALE_FACTOR=%r: the multi-scale test runs through step_multiscale() / "
+                               "step_device_multiscale()" % (self.scales,))
+        key = (n, s_h, s_w, dtype, self._final is not None, det_hw)
         st = self._state.get(key)
         if st is None:
             J = self.params.num_joints
             T = 2 if self.flip else 1
-            Hd, Wd = (s_h, s_w) if self.project else (s_h // 2, s_w // 2)
+            Hd, Wd = det_hw if det_hw is not None else ((s_h, s_w) if self.project else (s_h // 2, s_w // 2))
             dev = self.device
             row = J * (3 + T)
             st = {
@@ -325,6 +347,58 @@ class LitePosePipeline(object):
         packed = self.step_device(x, plant)
         n = packed.shape[0]
         st = self._get_state(n, x.shape[2], x.shape[3], x.dtype, plant)
+        st["host"].copy_(packed, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.unpack(st["host"], st["row"], st["T"], self.fetch_overflow(st, st["host"]))
+
+    # -- multi-scale test (TEST.SCALE_FACTOR with several entries; reference valid.py:198-229) ----------------------------
+    def step_device_multiscale(self, xs, plant=None):
+        """``xs``: {scale: frames [N,3,Hs,Ws] on the device} - for every scale of TEST.SCALE_FACTOR the batch resized
+        as resize_align_multi_scale does (litepose_b200.lib.utils.transforms.resize_align_normalize_device produces
+        it on the device).  Per scale, largest first: both network passes, then ONE glue launch (lp_glue_scale_f32)
+        that resamples the scale's flip-averaged heat-maps to the common size and accumulates them
+        (aggregate_results, lib/core/inference.py:176-208); the tags come from the scale-1 pass; the sum is divided by
+        the number of scales by the last launch (valid.py:223).  Common size = base_size (the scale-1 frames) with
+        PROJECT2IMAGE, else the first scale's heat-map size.  Then the device parser, as in step_device.
+        Launches run eagerly (no CUDA graph: one plan per scale).  Returns the packed device result."""
+        scales = self.scales
+        missing = [s for s in scales if s not in xs]
+        if missing:
+            raise ValueError("step_device_multiscale: no frames for scale(s) %r" % (missing,))
+        x1 = xs[1.0]
+        n = x1.shape[0]
+        big = xs[scales[0]]
+        det_hw = (x1.shape[2], x1.shape[3]) if self.project else (big.shape[2] // 2, big.shape[3] // 2)
+        st = self._get_state(n, x1.shape[2], x1.shape[3], x1.dtype, plant, det_hw=det_hw)
+        J = self.params.num_joints
+        det, tag = st["det"], st["tag"]
+        self.engine.use_graphs = False
+        stream = torch.cuda.current_stream().cuda_stream
+        for i, s in enumerate(scales):
+            x = xs[s]
+            if x.shape[0] != n or x.shape[2] % 64 or x.shape[3] % 64:
+                raise ValueError("step_device_multiscale: scale %r frames %r (batch %d, sides multiples of 64 expected)"
+                                 % (s, tuple(x.shape), n))
+            o, f = self._network_part(st, x)
+            _, _, h, w = o[0].shape
+            _lib.check(self.lib.lp_glue_scale_f32(
+                o[0].data_ptr(), o[1].data_ptr(), f[0].data_ptr() if self.flip else None,
+                f[1].data_ptr() if self.flip else None, self.fidx.data_ptr(), n, J, h, w, 1 if self.flip else 0,
+                det_hw[0], det_hw[1], 1 if i > 0 else 0, float(len(scales)) if i == len(scales) - 1 else 1.0,
+                det.data_ptr(), tag.data_ptr() if s == 1.0 else None, stream), "lp_glue_scale_f32")
+        if st["plant"] is not None:
+            st["plant"].apply(det, tag)
+        return self._parser_part(st, det, tag, st["packed"])
+
+    def step_multiscale(self, frames, plant=None):
+        """Public blocking call of the multi-scale test: {scale: pinned host frames} in, host result out (the list
+        over images of (ans [P,J,3+T], scores, P), as step())."""
+        xs = {float(s): f.to(self.device, non_blocking=True) for s, f in frames.items()}
+        packed = self.step_device_multiscale(xs, plant)
+        x1 = xs[1.0]
+        big = xs[self.scales[0]]
+        det_hw = (x1.shape[2], x1.shape[3]) if self.project else (big.shape[2] // 2, big.shape[3] // 2)
+        st = self._get_state(x1.shape[0], x1.shape[2], x1.shape[3], x1.dtype, plant, det_hw=det_hw)
         st["host"].copy_(packed, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.unpack(st["host"], st["row"], st["T"], self.fetch_overflow(st, st["host"]))

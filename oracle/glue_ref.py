@@ -2,8 +2,8 @@
 
 CPU fp32 restatement of the test-time glue between model and parser:
 ``get_multi_stage_outputs`` (reference lib/core/inference.py:75-173) and
-``aggregate_results`` (:176-208) for the single-scale evaluation config
-(SCALE_FACTOR [1]); floating point, so torch fp32 CPU ops.
+``aggregate_results`` (:176-208), single scale (``aggregate``) and the multi-scale loop of
+valid.py:205-225 (``multi_scale``); floating point, so torch fp32 CPU ops.
 
 The x2 bilinear resamples are written out explicitly (SURVEY Appendix A.4:
 ``align_corners=False``; out[2m] = .25*x[m-1] + .75*x[m], out[2m+1] = .75*x[m] +
@@ -91,3 +91,32 @@ def aggregate(cfg, heatmaps, tags):
     hm = (heatmaps[0] + heatmaps[1]) / 2.0 if cfg.TEST.FLIP_TEST else heatmaps[0]
     hm = hm / float(len(cfg.TEST.SCALE_FACTOR))
     return hm, torch.cat(tags_list, dim=4)
+
+
+def aggregate_results(cfg, scale_factor, final_heatmaps, tags_list, heatmaps, tags):
+    """inference.py:176-208, one scale of the multi-scale loop."""
+    if scale_factor == 1 or len(cfg.TEST.SCALE_FACTOR) == 1:
+        if final_heatmaps is not None and not cfg.TEST.PROJECT2IMAGE:
+            tags = [bilinear(t, final_heatmaps.shape[2:4]) for t in tags]
+        for t in tags:
+            tags_list.append(t.unsqueeze(4))
+    avg = (heatmaps[0] + heatmaps[1]) / 2.0 if cfg.TEST.FLIP_TEST else heatmaps[0]
+    if final_heatmaps is None:
+        final_heatmaps = avg
+    elif cfg.TEST.PROJECT2IMAGE:
+        final_heatmaps = final_heatmaps + avg
+    else:
+        final_heatmaps = final_heatmaps + bilinear(avg, final_heatmaps.shape[2:4])
+    return final_heatmaps, tags_list
+
+
+def multi_scale(cfg, model, images, base_size):
+    """valid.py:205-225: ``images`` maps every scale of TEST.SCALE_FACTOR to its resized image batch; scales are
+    visited largest first; returns (final_heatmaps [N,J,H,W], tags [N,J,H,W,T])."""
+    final, tags_list = None, []
+    scales = sorted(cfg.TEST.SCALE_FACTOR, reverse=True)
+    for s in scales:
+        _, hms, tgs = multi_stage_outputs(cfg, model, images[s], cfg.TEST.FLIP_TEST, cfg.TEST.PROJECT2IMAGE, base_size)
+        final, tags_list = aggregate_results(cfg, s, final, tags_list, hms, tgs)
+    final = final / float(len(scales))
+    return final, torch.cat(tags_list, dim=4)

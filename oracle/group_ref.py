@@ -287,8 +287,13 @@ class HeatmapParser(object):
         scores = [i[:, 2].mean() for i in ans[0]]
         if refine_:
             ans = ans[0]
+            tag0 = tag[0]
+            if not self.tag_per_joint:
+                # group.py:283-286 means to tile the shared tag map over the joints (the reference's own lines stop on
+                # the unassigned name `tag_numpy` there; the tiling is the evident intent)
+                tag0 = np.tile(tag0, (self.params.num_joints,) + (1,) * (tag0.ndim - 1))
             for i in range(len(ans)):
-                ans[i] = refine(det[0], tag[0], ans[i])
+                ans[i] = refine(det[0], tag0, ans[i])
             ans = [ans]
         return ans, scores
 

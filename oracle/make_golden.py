@@ -111,6 +111,61 @@ def golden_glue():
                             final_heatmaps=fh.numpy(), tags=tags.numpy())
 
 
+MULTISCALE_CASES = [
+    # name, SCALE_FACTOR, PROJECT2IMAGE, FLIP_TEST, input_size (square images), seed
+    ("ms_1_2_proj1", [1, 2], True, True, 64, 41),
+    ("ms_05_1_proj0", [0.5, 1], False, True, 128, 42),
+]
+
+
+class FakeScaleModel(object):
+    """Seeded random network outputs shaped by the image it is given: [N,2J,H/4,W/4], [N,J,H/2,W/2]; ``log`` keeps
+    every call's outputs in call order (largest scale first, plain pass then mirrored pass)."""
+
+    def __init__(self, nj, seed):
+        self.nj, self.g, self.log = nj, torch.Generator().manual_seed(seed), []
+
+    def __call__(self, img):
+        n, _, h, w = img.shape
+        outs = [torch.randn(n, 2 * self.nj, h // 4, w // 4, generator=self.g),
+                torch.randn(n, self.nj, h // 2, w // 2, generator=self.g)]
+        self.log.append(outs)
+        return [o.clone() for o in outs]
+
+
+def multiscale_inputs(cfg, size):
+    """valid.py:198-212 for a square ``size`` x ``size`` image: base_size and the (empty) resized image per scale."""
+    from litepose_b200.lib.utils.transforms import get_multi_scale_size
+    img = np.zeros((size, size, 3), np.uint8)
+    smin = min(cfg.TEST.SCALE_FACTOR)
+    base, _, _ = get_multi_scale_size(img, cfg.DATASET.INPUT_SIZE, 1.0, smin)
+    images = {}
+    for s in cfg.TEST.SCALE_FACTOR:
+        (w, h), _, _ = get_multi_scale_size(img, cfg.DATASET.INPUT_SIZE, s, smin)
+        images[s] = torch.zeros(1, 3, h, w)
+    return base, images
+
+
+def golden_glue_multiscale():
+    """The multi-scale loop of valid.py:205-225 run with the reference's own get_multi_stage_outputs / aggregate_results
+    on a seeded fake model; inputs are reproduced from the seed in the tests (digest stored)."""
+    ns = refshim.load()
+    for name, scales, proj, flip, size, seed in MULTISCALE_CASES:
+        cfg = get_cfg(input_size=size, flip_test=flip, project2image=proj)
+        cfg.TEST.SCALE_FACTOR = list(scales)
+        base, images = multiscale_inputs(cfg, size)
+        fake = FakeScaleModel(cfg.DATASET.NUM_JOINTS, seed)
+        final, tags_list = None, []
+        for s in sorted(cfg.TEST.SCALE_FACTOR, reverse=True):
+            _, h, t = ns.inference.get_multi_stage_outputs(cfg, fake, images[s], flip, proj, base)
+            final, tags_list = ns.inference.aggregate_results(cfg, s, final, tags_list, h, t)
+        final = final / float(len(cfg.TEST.SCALE_FACTOR))
+        tags = torch.cat(tags_list, dim=4)
+        dig = hashlib.sha256(b"".join(o.numpy().tobytes() for outs in fake.log for o in outs)).hexdigest()
+        np.savez_compressed(os.path.join(OUT, "glue_%s.npz" % name), in_digest=np.array(dig),
+                            final_heatmaps=final.numpy(), tags=tags.numpy())
+
+
 PARSER_CASES = [
     # name, J-dataset, h, w, T, people, seed
     ("p5_128_t2", "crowd_pose", 128, 128, 2, 5, 0),
@@ -149,6 +204,40 @@ def golden_parser(only=None):
         np.savez_compressed(os.path.join(OUT, "parser_%s.npz" % name), **blob)
 
 
+def shared_tag_case(nj, h, w, t, people, seed):
+    """Inputs of the MODEL.TAG_PER_JOINT=False case: the planted crowd with ONE tag map shared by all joints (every pixel
+    takes the tag of the joint plane with the largest heat there)."""
+    det, tag = synth.plant_crowd(nj, h, w, t, num_people=people, seed=seed)
+    pick = det.argmax(axis=0)[None, :, :, None]
+    shared = np.take_along_axis(tag, np.broadcast_to(pick, (1, h, w, t)), axis=0)
+    return det, np.ascontiguousarray(shared)
+
+
+def golden_parser_shared_tag():
+    """lib/core/group.py:150-152 (TAG_PER_JOINT=False).  With refine the reference stops on an unassigned name
+    (group.py:283-286) as soon as one person is found - recorded here, so only refine=False outputs exist."""
+    ns = refshim.load()
+    cfg = get_cfg(input_size=256)
+    cfg.MODEL.TAG_PER_JOINT = False
+    nj = cfg.DATASET.NUM_JOINTS
+    det, tag = shared_tag_case(nj, 128, 160, 2, 6, 31)
+    dt, tt = torch.from_numpy(det)[None], torch.from_numpy(tag)[None]
+    rp = ns.group.HeatmapParser(cfg)
+    top = rp.top_k(dt, tt)
+    blob = {"in_digest": np.array(hashlib.sha256(det.tobytes() + tag.tobytes()).hexdigest()),
+            "val_k": top["val_k"], "loc_k": top["loc_k"], "tag_k": top["tag_k"]}
+    for adj in (True, False):
+        ans, scores = rp.parse(dt.clone(), tt.clone(), adj, False)
+        blob["ans_a%d_r0" % adj] = np.array(ans[0], dtype=np.float32).reshape(-1, nj, 5)
+        blob["scores_a%d_r0" % adj] = np.array(scores, dtype=np.float32)
+    try:
+        rp.parse(dt.clone(), tt.clone(), True, True)
+        blob["refine_raises"] = np.array("")
+    except NameError as e:
+        blob["refine_raises"] = np.array("NameError: %s" % e)
+    np.savez_compressed(os.path.join(OUT, "parser_shared_tag_p6.npz"), **blob)
+
+
 def golden_munkres():
     """Self-pinned restatement outputs on degenerate matrices (parity unpinned vs
     PyPI munkres, see oracle/munkres_ref.py) + the reference's own cost recipe."""
@@ -178,10 +267,15 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     if len(sys.argv) > 2 and sys.argv[1] == "--parser-only":       # regenerate selected parser cases only
         golden_parser(only=set(sys.argv[2:]))
+    elif len(sys.argv) > 1 and sys.argv[1] == "--new-r2":          # fixtures added in round 2 (others untouched)
+        golden_parser_shared_tag()
+        golden_glue_multiscale()
     else:
         golden_model()
         golden_glue()
         golden_parser()
+        golden_parser_shared_tag()
+        golden_glue_multiscale()
         golden_munkres()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -198,3 +198,138 @@ def test_parser_bench_geometry_vs_oracle(size, n, people, min_found):
         assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(exp[i][1], np.float32))
         found.append(e.shape[0])
     assert max(found) >= min_found, found
+
+
+# ---- round 2: wide matcher (MAX_NUM_PEOPLE up to 64), shared tag map, multi-scale glue -------------------------------
+@pytest.fixture
+def wide_matcher():
+    """routes every lp_tag_match_f32 call through the two-columns-per-lane kernel (read per call by the library)"""
+    os.environ["LP_MATCH_WIDE"] = "1"
+    yield
+    os.environ.pop("LP_MATCH_WIDE", None)
+
+
+@pytest.mark.parametrize("case", [c for c in PARSER_CASES if c[0] in ("p5_128_t2", "p30_256_t2", "p30_256_t1",
+                                                                      "coco_p8_128_t2", "p30_640_t2")],
+                         ids=lambda c: c[0])
+def test_parser_golden_wide_matcher(golden_dir, case, wide_matcher):
+    """The reference goldens (K = 30) through the 64-wide matcher kernel: bit-exact like the 32-wide one."""
+    test_parser_golden(golden_dir, case)
+
+
+@pytest.mark.parametrize("k,people,size", [(48, 40, 320), (64, 60, 384), (33, 12, 192)])
+def test_parser_more_than_32_people(k, people, size):
+    """DATASET.MAX_NUM_PEOPLE above the warp width (the reference has no limit: lib/config/default.py, group.py:54):
+    top-K with K > 32 and cost matrices up to 64 x 64, bit-exact against the oracle."""
+    cfg = get_cfg(input_size=size)
+    cfg.DATASET.MAX_NUM_PEOPLE = k
+    n = 2
+    det, tag = synth.plant_crowd_batch(n, 14, size, size, 2, num_people=people, seed=700 + k)
+    p = _parser(cfg)
+    got = p.parse_batch(torch.from_numpy(det).cuda(), torch.from_numpy(tag).cuda(), True, True)
+    exp = group_ref.HeatmapParser(cfg).parse_batch(det.copy(), tag.copy(), True, True)
+    found = []
+    for i in range(n):
+        a = np.asarray(got[i][0][0], np.float32).reshape(-1, 14, 5)
+        e = np.asarray(exp[i][0][0], np.float32).reshape(-1, 14, 5)
+        assert a.shape == e.shape, (i, a.shape, e.shape)
+        assert np.array_equal(a, e), i
+        assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(exp[i][1], np.float32))
+        found.append(e.shape[0])
+    assert max(found) >= min(people, 33), found
+
+
+def test_parser_shared_tag_golden(golden_dir):
+    """MODEL.TAG_PER_JOINT=False (one tag map shared by all joints, reference group.py:150-152): top_k and the parse
+    without refine against the reference's outputs; with refine (where the reference itself stops on an unassigned
+    name, recorded in the fixture) against the oracle on the tiled maps."""
+    from oracle.make_golden import shared_tag_case
+    z = np.load(os.path.join(golden_dir, "parser_shared_tag_p6.npz"))
+    cfg = get_cfg(input_size=256)
+    cfg.MODEL.TAG_PER_JOINT = False
+    det, tag = shared_tag_case(14, 128, 160, 2, 6, 31)
+    assert hashlib.sha256(det.tobytes() + tag.tobytes()).hexdigest() == str(z["in_digest"])
+    assert str(z["refine_raises"]).startswith("NameError")
+    p = _parser(cfg)
+    dd, td = torch.from_numpy(det)[None].cuda(), torch.from_numpy(tag)[None].cuda()
+    assert_topk_equal(p.top_k(dd, td), {k: z[k] for k in ("val_k", "loc_k", "tag_k")}, "shared tag")
+    for adj in (True, False):
+        ans, scores = p.parse(dd, td, adj, False)
+        a = np.asarray(ans[0], np.float32).reshape(-1, 14, 5)
+        assert np.array_equal(a, z["ans_a%d_r0" % adj])
+        assert np.array_equal(np.asarray(scores, np.float32), z["scores_a%d_r0" % adj])
+    ans, scores = p.parse(dd, td, True, True)
+    ea, es = group_ref.HeatmapParser(cfg).parse(det[None].copy(), tag[None].copy(), True, True)
+    assert np.array_equal(np.asarray(ans[0], np.float32).reshape(-1, 14, 5), np.asarray(ea[0], np.float32).reshape(-1, 14, 5))
+    assert np.array_equal(np.asarray(scores, np.float32), np.asarray(es, np.float32))
+
+
+def _glue_scales_device(cfg, log, base_wh, first_hw):
+    """the multi-scale loop through lp_glue_scale_f32: ``log`` = per scale (largest first) [plain outs, flipped outs]"""
+    lib = _lib.load()
+    flip = bool(cfg.TEST.FLIP_TEST)
+    scales = sorted(cfg.TEST.SCALE_FACTOR, reverse=True)
+    J = cfg.DATASET.NUM_JOINTS
+    n = log[0][0].shape[0]
+    Hd, Wd = (base_wh[1], base_wh[0]) if cfg.TEST.PROJECT2IMAGE else first_hw
+    T = 2 if flip else 1
+    det = torch.full((n, J, Hd, Wd), float("nan"), device="cuda")
+    tag = torch.full((n, J, Hd, Wd, T), float("nan"), device="cuda")
+    fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device="cuda")
+    keep = []
+    per = 2 if flip else 1
+    for i, s in enumerate(scales):
+        a = [t.cuda() for t in log[i * per]]
+        b = [t.cuda() for t in log[i * per + 1]] if flip else [None, None]
+        keep.append((a, b))
+        h, w = a[0].shape[2], a[0].shape[3]
+        _lib.check(lib.lp_glue_scale_f32(a[0].data_ptr(), a[1].data_ptr(), _lib.ptr(b[0]), _lib.ptr(b[1]), fidx.data_ptr(),
+                                         n, J, h, w, 1 if flip else 0, Hd, Wd, 1 if i > 0 else 0,
+                                         float(len(scales)) if i == len(scales) - 1 else 1.0, det.data_ptr(),
+                                         tag.data_ptr() if s == 1 else None, torch.cuda.current_stream().cuda_stream),
+                   "lp_glue_scale_f32")
+    torch.cuda.synchronize()
+    return det.cpu(), tag.cpu()
+
+
+def test_glue_multiscale_golden(golden_dir):
+    """valid.py:205-225 with several TEST.SCALE_FACTOR entries: one lp_glue_scale_f32 launch per scale against the
+    outputs of the reference's own get_multi_stage_outputs / aggregate_results loop."""
+    from oracle.make_golden import MULTISCALE_CASES, FakeScaleModel, multiscale_inputs
+    for name, scales, proj, flip, size, seed in MULTISCALE_CASES:
+        z = np.load(os.path.join(golden_dir, "glue_%s.npz" % name))
+        cfg = get_cfg(input_size=size, flip_test=flip, project2image=proj)
+        cfg.TEST.SCALE_FACTOR = list(scales)
+        base, images = multiscale_inputs(cfg, size)
+        fake = FakeScaleModel(cfg.DATASET.NUM_JOINTS, seed)
+        for s in sorted(scales, reverse=True):
+            for _ in range(2 if flip else 1):
+                fake(images[s])
+        dig = hashlib.sha256(b"".join(o.numpy().tobytes() for outs in fake.log for o in outs)).hexdigest()
+        assert dig == str(z["in_digest"]), "seeded inputs differ from the ones the fixture was generated with"
+        first = images[max(scales)]
+        det, tag = _glue_scales_device(cfg, fake.log, base, (first.shape[2] // 2, first.shape[3] // 2))
+        ed, et = z["final_heatmaps"], z["tags"]
+        assert det.shape == ed.shape and tag.shape == et.shape
+        assert np.abs(det.numpy() - ed).max() <= 1e-5 * max(1.0, np.abs(ed).max()), name
+        assert np.abs(tag.numpy() - et).max() <= 1e-5 * max(1.0, np.abs(et).max()), name
+
+
+@pytest.mark.parametrize("scales,proj,hw", [([0.75, 1, 1.25], True, (192, 256)), ([1, 1.5, 2.5], True, (128, 128)),
+                                            ([0.5, 1, 2], False, (128, 192)), ([1, 2], True, (64, 64))])
+def test_glue_multiscale_ratios_vs_oracle(scales, proj, hw):
+    """projection ratios other than x2 / x4 (1.6x, 1.33x, identity, 0.8x shrink), non-square frames, three scales"""
+    from oracle.make_golden import FakeScaleModel
+    cfg = get_cfg(input_size=hw[0], flip_test=True, project2image=proj)
+    cfg.TEST.SCALE_FACTOR = list(scales)
+    smin = min(scales)
+    images = {s: torch.zeros(2, 3, int(round(hw[0] * s / 64)) * 64, int(round(hw[1] * s / 64)) * 64) for s in scales}
+    images[1] = torch.zeros(2, 3, hw[0], hw[1])
+    base = (hw[1], hw[0])
+    fake = FakeScaleModel(14, 5)
+    ed, et = glue_ref.multi_scale(cfg, fake, images, base)
+    first = images[max(scales)]
+    det, tag = _glue_scales_device(cfg, fake.log, base, (first.shape[2] // 2, first.shape[3] // 2))
+    assert det.shape == ed.shape and tag.shape == et.shape, (det.shape, ed.shape, smin)
+    assert (det - ed).abs().max().item() <= 1e-5 * max(1.0, ed.abs().max().item())
+    assert (tag - et).abs().max().item() <= 1e-5 * max(1.0, et.abs().max().item())

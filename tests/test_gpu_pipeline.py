@@ -104,12 +104,20 @@ def test_unsupported_cfg_is_rejected():
     cfg = get_cfg(input_size=128)
     torch.manual_seed(0)
     model = get_pose_net(cfg, False, get_arch("XS")).eval().cuda()
-    for mutate in (lambda c: setattr(c.TEST, "SCALE_FACTOR", [0.5, 1, 2]), lambda c: setattr(c.DATASET, "WITH_CENTER", True),
+    for mutate in (lambda c: setattr(c.MODEL, "TAG_PER_JOINT", False), lambda c: setattr(c.DATASET, "WITH_CENTER", True),
                    lambda c: setattr(c.TEST, "WITH_AE", (True, True))):
         c = get_cfg(input_size=128)
         mutate(c)
         with pytest.raises(NotImplementedError):
             LitePosePipeline(model, c)
+    c = get_cfg(input_size=128)
+    c.TEST.SCALE_FACTOR = [0.5, 2]            # the reference needs the scale-1 pass for the tags (valid.py:224)
+    with pytest.raises(ValueError):
+        LitePosePipeline(model, c)
+    c.TEST.SCALE_FACTOR = [0.5, 1]
+    pipe = LitePosePipeline(model, c)
+    with pytest.raises(RuntimeError):         # the single-scale entry points refuse a multi-scale cfg
+        pipe.step(synth.make_frames(1, 128, seed=1).half().pin_memory())
 
 
 def test_plant_change_recaptures_graph():
@@ -150,3 +158,45 @@ def test_submit_collect_equals_step():
         assert [r[2] for r in g] == [r[2] for r in e]
         for x, y in zip(g, e):
             assert np.array_equal(x[0], y[0]) and np.array_equal(np.asarray(x[1]), np.asarray(y[1]))
+
+
+@pytest.mark.parametrize("scales,proj", [([0.5, 1, 2], True), ([1, 2], False)])
+def test_multiscale_step_vs_oracle(scales, proj):
+    """TEST.SCALE_FACTOR with several entries (reference valid.py:198-229): per scale two network passes + one
+    accumulating glue launch, then the parser.  Maps within the model tolerance of the fp32 oracle loop
+    (oracle/glue_ref.multi_scale on oracle/model_ref.forward); keypoints bit-exactly the oracle parser's answer on the
+    maps the device produced."""
+    from oracle import glue_ref, model_ref
+    n, size = 2, 128
+    cfg = get_cfg(input_size=size, project2image=proj)
+    cfg.TEST.SCALE_FACTOR = list(scales)
+    arch = get_arch("XS")
+    torch.manual_seed(0)
+    model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, arch), 1)).eval()
+    sd = {k: v.float().clone() for k, v in model.state_dict().items()}
+    frames = {float(s): synth.make_frames(n, int(size * s), seed=40 + i) for i, s in enumerate(scales)}
+    pipe = LitePosePipeline(model.cuda(), cfg, use_graphs=True)
+    big = int(size * max(scales))
+    Hd = size if proj else big // 2
+    plant_dev = PlantedCrowd(n, 14, Hd, Hd, 2, num_people=3, seed=9, device="cuda")
+    plant_cpu = PlantedCrowd(n, 14, Hd, Hd, 2, num_people=3, seed=9, device="cpu")
+    got = pipe.step_multiscale({s: f.half().pin_memory() for s, f in frames.items()}, plant_dev)
+    st = pipe._get_state(n, size, size, torch.float16, plant_dev, det_hw=(Hd, Hd))
+    det_g, tag_g = st["det"].cpu().numpy(), st["tag"].cpu().numpy()
+    with torch.no_grad():
+        det_o, tag_o = glue_ref.multi_scale(cfg, lambda im: model_ref.forward(sd, arch, im), frames, (size, size))
+        det_o, tag_o = det_o.contiguous(), tag_o.contiguous()
+        det_raw, tag_raw = det_o.clone(), tag_o.clone()
+        plant_cpu.apply(det_o, tag_o)
+    assert det_g.shape == tuple(det_o.shape) and tag_g.shape == tuple(tag_o.shape)
+    for name, g, o, raw in (("det", det_g, det_o.numpy(), det_raw.numpy()), ("tag", tag_g, tag_o.numpy(), tag_raw.numpy())):
+        err = np.abs(g - o).max()
+        lim = 2e-3 * np.abs(raw).max() + 1e-4
+        assert err <= lim, "%s: %.3e > %.3e" % (name, err, lim)
+    op = group_ref.HeatmapParser(cfg)
+    for i in range(n):
+        ans, scores = op.parse(det_g[i:i + 1].copy(), tag_g[i:i + 1].copy(), True, True)
+        e = np.asarray(ans[0], np.float32).reshape(-1, 14, 5)
+        assert got[i][2] == e.shape[0] and e.shape[0] >= 3
+        assert np.array_equal(got[i][0], e), i
+        assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(scores, np.float32))

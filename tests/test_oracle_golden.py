@@ -101,3 +101,37 @@ def test_parser(golden_dir, case):
 
 def test_golden_present(golden_dir):
     assert len(glob.glob(os.path.join(golden_dir, "*.npz"))) >= 15
+
+
+def test_glue_multiscale(golden_dir):
+    """oracle/glue_ref.multi_scale (valid.py:205-225 + inference.py:176-208) against the outputs of the reference's own loop"""
+    from oracle.make_golden import MULTISCALE_CASES, FakeScaleModel, multiscale_inputs
+    for name, scales, proj, flip, size, seed in MULTISCALE_CASES:
+        z = np.load(os.path.join(golden_dir, "glue_%s.npz" % name))
+        cfg = get_cfg(input_size=size, flip_test=flip, project2image=proj)
+        cfg.TEST.SCALE_FACTOR = list(scales)
+        base, images = multiscale_inputs(cfg, size)
+        fake = FakeScaleModel(cfg.DATASET.NUM_JOINTS, seed)
+        fh, tg = glue_ref.multi_scale(cfg, fake, images, base)
+        dig = hashlib.sha256(b"".join(o.numpy().tobytes() for outs in fake.log for o in outs)).hexdigest()
+        assert dig == str(z["in_digest"])
+        assert np.allclose(fh.numpy(), z["final_heatmaps"], atol=2e-6), name
+        assert np.allclose(tg.numpy(), z["tags"], atol=2e-6), name
+
+
+def test_parser_shared_tag(golden_dir):
+    """MODEL.TAG_PER_JOINT=False: oracle top_k / parse (no refine) against the reference's outputs"""
+    from oracle.make_golden import shared_tag_case
+    z = np.load(os.path.join(golden_dir, "parser_shared_tag_p6.npz"))
+    cfg = get_cfg(input_size=256)
+    cfg.MODEL.TAG_PER_JOINT = False
+    det, tag = shared_tag_case(14, 128, 160, 2, 6, 31)
+    assert hashlib.sha256(det.tobytes() + tag.tobytes()).hexdigest() == str(z["in_digest"])
+    p = group_ref.HeatmapParser(cfg)
+    assert_topk_equal(p.top_k(det[None], tag[None]), {k: z[k] for k in ("val_k", "loc_k", "tag_k")}, "shared tag")
+    for adj in (True, False):
+        ans, scores = p.parse(det[None].copy(), tag[None].copy(), adj, False)
+        assert np.array_equal(np.array(ans[0], dtype=np.float32).reshape(-1, 14, 5), z["ans_a%d_r0" % adj])
+        assert np.array_equal(np.array(scores, np.float32), z["scores_a%d_r0" % adj])
+    ans, _ = p.parse(det[None].copy(), tag[None].copy(), True, True)      # the tiled-tag refine of the oracle runs
+    assert np.array(ans[0]).shape[1:] == (14, 5)
