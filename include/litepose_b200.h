@@ -259,19 +259,27 @@ int lp_glue_f32(const float* o0, const float* o1, const float* f0, const float* 
                 const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd, int Wd,
                 float* det, float* tag, lp_stream_t stream);
 
-/* Multi-scale test (TEST.SCALE_FACTOR with more than one entry; reference valid.py:205-225 +
- * aggregate_results lib/core/inference.py:176-208): ONE call per scale, largest scale first, on
- * that scale's network outputs (h, w follow the scale; Hd, Wd are the common size: base_size
- * with PROJECT2IMAGE, else the size of the first scale's heat-maps).  The scale's flip-averaged
- * heat-map, resampled to (Hd,Wd), is stored (accumulate == 0: first scale) or added to det
- * (`final_heatmaps += ...`); divide_by != 1 divides the sum afterwards
- * (`final_heatmaps / len(SCALE_FACTOR)`, valid.py:223: pass it with the last scale).  tag is
- * written (resampled to (Hd,Wd)) only for the scale == 1 call; pass NULL for the other scales
- * (inference.py:179-190).  Projection ratios down to a 4.6x shrink are supported. */
+/* General form of the glue (every cfg branch of lib/core/inference.py:75-208 for the LitePose head
+ * layout) and one scale of the multi-scale test (reference valid.py:205-225 + aggregate_results,
+ * inference.py:176-208).
+ *   model_joints: DATASET.NUM_JOINTS = heat channels of o0 / o1 (it counts the centre joint when
+ *     DATASET.WITH_CENTER is on, lib/config/default.py:175-177); J <= model_joints joints are
+ *     written (J = model_joints - 1 with TEST.IGNORE_CENTER, inference.py:147-150); flip_index
+ *     has model_joints entries.
+ *   tag_shared: MODEL.TAG_PER_JOINT off - o0 = [model_joints heat | ONE tag map], the tag map is
+ *     not permuted in the flip pass (inference.py:141-144) and tag is [N,1,Hd,Wd,T].
+ *   Multi-scale: ONE call per scale, largest scale first, on that scale's network outputs (h, w
+ *     follow the scale; Hd, Wd are the common size: base_size with PROJECT2IMAGE, else the size of
+ *     the first scale's heat-maps).  The scale's flip-averaged heat-map, resampled to (Hd,Wd), is
+ *     stored (accumulate == 0: first scale) or added to det (`final_heatmaps += ...`); divide_by
+ *     != 1 divides the sum afterwards (`final_heatmaps / len(SCALE_FACTOR)`, valid.py:223: pass
+ *     it with the last scale).  tag is written (resampled to (Hd,Wd)) only by the scale == 1
+ *     call; pass NULL for the other scales (inference.py:179-190).
+ * Single scale: accumulate 0, divide_by 1.  Projection ratios down to a 4.6x shrink. */
 int lp_glue_scale_f32(const float* o0, const float* o1, const float* f0, const float* f1,
-                      const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd,
-                      int Wd, int accumulate, float divide_by, float* det, float* tag,
-                      lp_stream_t stream);
+                      const int32_t* flip_index, int N, int J, int model_joints, int tag_shared,
+                      int h, int w, int flip, int Hd, int Wd, int accumulate, float divide_by,
+                      float* det, float* tag, lp_stream_t stream);
 
 /* ---- per-step host payload ------------------------------------------------------
  * What HeatmapParser.parse hands back to valid.py:227 (lib/core/group.py:269-291), for a whole

@@ -67,7 +67,7 @@ SIGNATURES = {
     "lp_adjust_refine_workspace_bytes": (_sz, [_i, _i, _i]),
     "lp_adjust_refine_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "lp_glue_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "lp_glue_scale_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "lp_glue_scale_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "lp_pack_payload_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "lp_plant_crowd_f32": (_i, [_vp, _vp, _vp, _c.c_int64, _vp, _vp, _vp, _c.c_int64, _vp]),
     "lp_warp_affine_normalize_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),

@@ -40,8 +40,8 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ p, int W, cons
 
 __global__ void __launch_bounds__(GL_THREADS)
 glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const float* __restrict__ f0,
-            const float* __restrict__ f1, const int32_t* __restrict__ flip_index, int J, int h, int w, int flip, int Hd,
-            int Wd, int tiles_x, int to, int accumulate, float divide_by, float* __restrict__ det,
+            const float* __restrict__ f1, const int32_t* __restrict__ flip_index, int J, int Jm, int tag_shared, int h, int w,
+            int flip, int Hd, int Wd, int tiles_x, int to, int accumulate, float divide_by, float* __restrict__ det,
             float* __restrict__ tag) {
     __shared__ float s_ha[GL_TM][GL_TM + 1], s_hf[GL_TM][GL_TM + 1], s_t0[GL_TM][GL_TM + 1], s_t1[GL_TM][GL_TM + 1];
     const int n = blockIdx.z, j = blockIdx.y;
@@ -63,16 +63,21 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
     const int mh = my1 - my0 + 1, mw = mx1 - mx0 + 1;   // <= GL_TM guaranteed by the host (choice of `to`) unless !project
     const float us_y = (float)h / (float)H2, us_x = (float)w / (float)W2;   // 0.5
 
+    // channel layout of the model outputs (pose_mobilenet.py:86-100): o0 = [Jm heat | Jm tags, or ONE tag map when
+    // MODEL.TAG_PER_JOINT is off], o1 = [Jm heat]; Jm > J when the centre joint is ignored (inference.py:147-150).  The
+    // shared tag map is written once (by the j == 0 blocks) and is not permuted in the flip pass (inference.py:141-144).
+    const int C0 = tag_shared ? Jm + 1 : 2 * Jm;
+    if (tag_shared && j != 0) tag = nullptr;
     const size_t hw = (size_t)h * w, HW2 = (size_t)H2 * W2;
-    const float* a_heat = o0 + ((size_t)n * 2 * J + j) * hw;
-    const float* a_tag = o0 + ((size_t)n * 2 * J + J + j) * hw;
-    const float* a_o1 = o1 + ((size_t)n * J + j) * HW2;
+    const float* a_heat = o0 + ((size_t)n * C0 + j) * hw;
+    const float* a_tag = o0 + ((size_t)n * C0 + Jm + (tag_shared ? 0 : j)) * hw;
+    const float* a_o1 = o1 + ((size_t)n * Jm + j) * HW2;
     const float *b_heat = nullptr, *b_tag = nullptr, *b_o1 = nullptr;
     if (flip) {
         const int fj = flip_index[j];
-        b_heat = f0 + ((size_t)n * 2 * J + fj) * hw;
-        b_tag = f0 + ((size_t)n * 2 * J + J + fj) * hw;
-        b_o1 = f1 + ((size_t)n * J + fj) * HW2;
+        b_heat = f0 + ((size_t)n * C0 + fj) * hw;
+        b_tag = f0 + ((size_t)n * C0 + Jm + (tag_shared ? 0 : fj)) * hw;
+        b_o1 = f1 + ((size_t)n * Jm + fj) * HW2;
     }
 
     if (project) {
@@ -93,7 +98,7 @@ glue_kernel(const float* __restrict__ o0, const float* __restrict__ o1, const fl
     }
 
     float* dplane = det + ((size_t)n * J + j) * Hd * Wd;
-    float* tplane = tag + ((size_t)n * J + j) * Hd * Wd * T;
+    float* tplane = tag ? tag + ((size_t)n * (tag_shared ? 1 : J) + j) * Hd * Wd * T : nullptr;
     const int th = oy1 - oy0 + 1, tw = ox1 - ox0 + 1;
 
     // multi-scale aggregation (inference.py:176-208): det accumulates over the scales, the division by the number of
@@ -303,13 +308,15 @@ static int glue_tile_side(int h, int w, int Hd, int Wd) {
 }
 
 static int glue_launch(const char* who, const float* o0, const float* o1, const float* f0, const float* f1,
-                       const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd, int Wd, int accumulate,
-                       float divide_by, float* det, float* tag, bool allow_x4, lp_stream_t stream) {
+                       const int32_t* flip_index, int N, int J, int Jm, int tag_shared, int h, int w, int flip, int Hd,
+                       int Wd, int accumulate, float divide_by, float* det, float* tag, bool allow_x4, lp_stream_t stream) {
     LP_CHECK_ARG(o0 && o1 && det, "%s: null pointer", who);
     LP_CHECK_ARG(!flip || (f0 && f1 && flip_index), "%s: flip pass needs f0, f1, flip_index", who);
     LP_CHECK_ARG(N > 0 && N <= 65535 && J > 0 && J <= 65535 && h > 0 && w > 0 && Hd > 0 && Wd > 0,
                  "%s: bad shape N=%d J=%d h=%d w=%d Hd=%d Wd=%d", who, N, J, h, w, Hd, Wd);
+    LP_CHECK_ARG(Jm >= J, "%s: model_joints=%d must be >= J=%d", who, Jm, J);
     LP_CHECK_ARG(divide_by > 0.f, "%s: divide_by must be > 0", who);
+    allow_x4 = allow_x4 && Jm == J && !tag_shared;
     const bool project = !(Hd == 2 * h && Wd == 2 * w);
     int to = GL_TO;
     if (project) {
@@ -330,8 +337,8 @@ static int glue_launch(const char* who, const float* o0, const float* o1, const 
     }
     const int tiles_x = (Wd + to - 1) / to, tiles_y = (Hd + to - 1) / to;
     dim3 grid(tiles_x * tiles_y, J, N);
-    glue_kernel<<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(o0, o1, f0, f1, flip_index, J, h, w, flip, Hd, Wd, tiles_x,
-                                                             to, accumulate, divide_by, det, tag);
+    glue_kernel<<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(o0, o1, f0, f1, flip_index, J, Jm, tag_shared ? 1 : 0, h, w, flip,
+                                                             Hd, Wd, tiles_x, to, accumulate, divide_by, det, tag);
     LP_LAUNCH_CHECK("glue_kernel");
     return LP_OK;
 }
@@ -340,12 +347,14 @@ extern "C" int lp_glue_f32(const float* o0, const float* o1, const float* f0, co
                            int N, int J, int h, int w, int flip, int Hd, int Wd, float* det, float* tag,
                            lp_stream_t stream) {
     LP_CHECK_ARG(tag, "lp_glue_f32: null pointer");
-    return glue_launch("lp_glue_f32", o0, o1, f0, f1, flip_index, N, J, h, w, flip, Hd, Wd, 0, 1.f, det, tag, true, stream);
+    return glue_launch("lp_glue_f32", o0, o1, f0, f1, flip_index, N, J, J, 0, h, w, flip, Hd, Wd, 0, 1.f, det, tag, true,
+                       stream);
 }
 
 extern "C" int lp_glue_scale_f32(const float* o0, const float* o1, const float* f0, const float* f1,
-                                 const int32_t* flip_index, int N, int J, int h, int w, int flip, int Hd, int Wd,
-                                 int accumulate, float divide_by, float* det, float* tag, lp_stream_t stream) {
-    return glue_launch("lp_glue_scale_f32", o0, o1, f0, f1, flip_index, N, J, h, w, flip, Hd, Wd, accumulate ? 1 : 0,
-                       divide_by, det, tag, !accumulate && divide_by == 1.f && tag != nullptr, stream);
+                                 const int32_t* flip_index, int N, int J, int model_joints, int tag_shared, int h, int w,
+                                 int flip, int Hd, int Wd, int accumulate, float divide_by, float* det, float* tag,
+                                 lp_stream_t stream) {
+    return glue_launch("lp_glue_scale_f32", o0, o1, f0, f1, flip_index, N, J, model_joints, tag_shared, h, w, flip, Hd, Wd,
+                       accumulate ? 1 : 0, divide_by, det, tag, !accumulate && divide_by == 1.f && tag != nullptr, stream);
 }

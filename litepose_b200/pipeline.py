@@ -104,6 +104,12 @@ class LitePosePipeline(object):
         self.project = bool(cfg.TEST.PROJECT2IMAGE)
         self.adjust, self.refine = bool(cfg.TEST.ADJUST), bool(cfg.TEST.REFINE)
         self.fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device=self.device)
+        # model channel layout (pose_mobilenet.py:86-100, lib/config/default.py:175-177): DATASET.NUM_JOINTS counts the
+        # centre joint when WITH_CENTER is on (the parser drops it with IGNORE_CENTER: Params.num_joints);
+        # TAG_PER_JOINT off = ONE tag map after the heat-maps
+        self.model_joints = int(cfg.DATASET.NUM_JOINTS)
+        self.tag_shared = not bool(cfg.MODEL.TAG_PER_JOINT)
+        self.canonical = self.model_joints == p.num_joints and not self.tag_shared
         self.use_graphs = use_graphs
         import os
         self.two_streams = os.environ.get("LP_TWO_STREAMS", "1") != "0"
@@ -119,21 +125,22 @@ class LitePosePipeline(object):
 
     @staticmethod
     def _validate_cfg(cfg):
-        """The fused glue kernel implements the shipped evaluation settings (experiments/*/mobile.yaml on top of
-        lib/config/default.py); anything else is rejected here instead of being silently ignored
-        (reference lib/core/inference.py:75-208 branches on every one of these keys)."""
+        """The fused glue kernels cover the cfg keys that lib/core/inference.py:75-208 branches on for the LitePose head
+        layout (two stages: heat + tags at 1/4, heat at 1/2): flip test, PROJECT2IMAGE, multi-scale, WITH_CENTER /
+        IGNORE_CENTER, TAG_PER_JOINT.  Other stage selections (WITH_HEATMAPS / WITH_AE other than the shipped
+        (True, True) / (True, False)) are rejected here instead of being silently ignored."""
         def bad(what):
             raise NotImplementedError("LitePosePipeline: %s is not supported by the fused glue kernel "
                                       "(use the reference's core.inference on the drop-in module instead)" % what)
+        if cfg.DATASET.WITH_CENTER and cfg.TEST.IGNORE_CENTER and not cfg.MODEL.TAG_PER_JOINT:
+            # the reference slices the last channel off the tags as well (inference.py:147-150): with ONE shared tag map
+            # nothing is left and its parser fails on the empty tensor - no behaviour to reproduce
+            bad("WITH_CENTER + IGNORE_CENTER with TAG_PER_JOINT=False (the reference drops the only tag map there)")
         scales = [float(v) for v in cfg.TEST.SCALE_FACTOR]
         if len(scales) != len(set(scales)) or 1.0 not in scales or min(scales) <= 0:
             # the reference takes the tags from the scale-1 pass only (inference.py:179-190): without it torch.cat of an
             # empty list fails at valid.py:224
             raise ValueError("TEST.SCALE_FACTOR=%r: distinct positive scales including 1 expected" % (scales,))
-        if cfg.DATASET.WITH_CENTER:
-            bad("DATASET.WITH_CENTER")
-        if not cfg.MODEL.TAG_PER_JOINT:
-            bad("MODEL.TAG_PER_JOINT=False")
         if tuple(cfg.LOSS.WITH_HEATMAPS_LOSS) != (True, True) or tuple(cfg.TEST.WITH_HEATMAPS) != (True, True):
             bad("WITH_HEATMAPS_LOSS / TEST.WITH_HEATMAPS other than (True, True)")
         if tuple(cfg.LOSS.WITH_AE_LOSS) != (True, False) or tuple(cfg.TEST.WITH_AE) != (True, False):
@@ -192,10 +199,16 @@ class LitePosePipeline(object):
         o0, o1 = o[0], o[1]
         n, _, h, w = o0.shape
         Hd, Wd = det.shape[2], det.shape[3]
-        _lib.check(self.lib.lp_glue_f32(o0.data_ptr(), o1.data_ptr(), f[0].data_ptr() if self.flip else None,
-                                        f[1].data_ptr() if self.flip else None, self.fidx.data_ptr(), n, J, h, w,
-                                        1 if self.flip else 0, Hd, Wd, det.data_ptr(), tag.data_ptr(),
-                                        torch.cuda.current_stream().cuda_stream), "lp_glue_f32")
+        fl = 1 if self.flip else 0
+        f0, f1 = (f[0].data_ptr(), f[1].data_ptr()) if self.flip else (None, None)
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.canonical:
+            _lib.check(self.lib.lp_glue_f32(o0.data_ptr(), o1.data_ptr(), f0, f1, self.fidx.data_ptr(), n, J, h, w, fl, Hd,
+                                            Wd, det.data_ptr(), tag.data_ptr(), stream), "lp_glue_f32")
+        else:
+            _lib.check(self.lib.lp_glue_scale_f32(o0.data_ptr(), o1.data_ptr(), f0, f1, self.fidx.data_ptr(), n, J,
+                                                  self.model_joints, 1 if self.tag_shared else 0, h, w, fl, Hd, Wd, 0, 1.0,
+                                                  det.data_ptr(), tag.data_ptr(), stream), "lp_glue_scale_f32")
         if st["plant"] is not None:
             st["plant"].apply(det, tag)
 
@@ -207,6 +220,10 @@ class LitePosePipeline(object):
     def _parser_part(self, st, det, tag, packed):
         """Device parser (+ get_final_preds) on det / tag -> packed fixed-size payload."""
         n = det.shape[0]
+        if self.tag_shared:
+            # MODEL.TAG_PER_JOINT off: the one tag map serves every joint (group.py:150-152); the parser kernels index
+            # [N,J,H,W,T], so the map is tiled here (one strided copy; not the shipped configuration)
+            tag = tag.expand(-1, det.shape[1], -1, -1, -1).contiguous()
         ans, num, scores = self.parser.run(det, tag, self.adjust, self.refine)
         if st["trans"] is not None:
             _lib.check(self.lib.lp_transform_preds_f32(ans.data_ptr(), num.data_ptr(), st["trans"].data_ptr(), n,
@@ -293,7 +310,7 @@ class LitePosePipeline(object):
                 "x": torch.empty((n, 3, s_h, s_w), dtype=dtype, device=dev),
                 "side": torch.cuda.Stream(device=dev),
                 "det": torch.empty((n, J, Hd, Wd), dtype=torch.float32, device=dev),
-                "tag": torch.empty((n, J, Hd, Wd, T), dtype=torch.float32, device=dev),
+                "tag": torch.empty((n, 1 if self.tag_shared else J, Hd, Wd, T), dtype=torch.float32, device=dev),
                 "packed": torch.zeros((n, self.keep * row + self.keep + 1), dtype=torch.float32, device=dev),
                 "host": torch.empty((n, self.keep * row + self.keep + 1), dtype=torch.float32).pin_memory(),
                 "row": row, "T": T, "graph": None, "plant": plant, "trans": None, "full": None, "ov": None,
@@ -383,8 +400,9 @@ class LitePosePipeline(object):
             _, _, h, w = o[0].shape
             _lib.check(self.lib.lp_glue_scale_f32(
                 o[0].data_ptr(), o[1].data_ptr(), f[0].data_ptr() if self.flip else None,
-                f[1].data_ptr() if self.flip else None, self.fidx.data_ptr(), n, J, h, w, 1 if self.flip else 0,
-                det_hw[0], det_hw[1], 1 if i > 0 else 0, float(len(scales)) if i == len(scales) - 1 else 1.0,
+                f[1].data_ptr() if self.flip else None, self.fidx.data_ptr(), n, J, self.model_joints,
+                1 if self.tag_shared else 0, h, w, 1 if self.flip else 0, det_hw[0], det_hw[1], 1 if i > 0 else 0,
+                float(len(scales)) if i == len(scales) - 1 else 1.0,
                 det.data_ptr(), tag.data_ptr() if s == 1.0 else None, stream), "lp_glue_scale_f32")
         if st["plant"] is not None:
             st["plant"].apply(det, tag)

@@ -122,12 +122,13 @@ class FakeScaleModel(object):
     """Seeded random network outputs shaped by the image it is given: [N,2J,H/4,W/4], [N,J,H/2,W/2]; ``log`` keeps
     every call's outputs in call order (largest scale first, plain pass then mirrored pass)."""
 
-    def __init__(self, nj, seed):
+    def __init__(self, nj, seed, tag_channels=None):
         self.nj, self.g, self.log = nj, torch.Generator().manual_seed(seed), []
+        self.nt = nj if tag_channels is None else tag_channels
 
     def __call__(self, img):
         n, _, h, w = img.shape
-        outs = [torch.randn(n, 2 * self.nj, h // 4, w // 4, generator=self.g),
+        outs = [torch.randn(n, self.nj + self.nt, h // 4, w // 4, generator=self.g),
                 torch.randn(n, self.nj, h // 2, w // 2, generator=self.g)]
         self.log.append(outs)
         return [o.clone() for o in outs]
@@ -164,6 +165,47 @@ def golden_glue_multiscale():
         dig = hashlib.sha256(b"".join(o.numpy().tobytes() for outs in fake.log for o in outs)).hexdigest()
         np.savez_compressed(os.path.join(OUT, "glue_%s.npz" % name), in_digest=np.array(dig),
                             final_heatmaps=final.numpy(), tags=tags.numpy())
+
+
+GLUE_CFG_CASES = [
+    # name, WITH_CENTER, IGNORE_CENTER, TAG_PER_JOINT, PROJECT2IMAGE, seed
+    ("center_ignored", True, True, True, True, 51),
+    ("center_kept", True, False, True, True, 52),
+    ("shared_tag", False, True, False, True, 53),
+    ("shared_tag_noproj", False, True, False, False, 54),
+]
+
+
+GLUE_CFG_SIZE = 32        # fake "image" side of the cfg-branch cases (the fake model only looks at the shape)
+
+
+def glue_cfg(with_center, ignore_center, tag_per_joint, proj, size=64, dataset="crowd_pose"):
+    """cfg as lib/config/default.py:175-177 leaves it: NUM_JOINTS counts the centre joint when WITH_CENTER is on"""
+    cfg = get_cfg(dataset=dataset, input_size=size, flip_test=True, project2image=proj)
+    cfg.DATASET.WITH_CENTER = with_center
+    if with_center:
+        cfg.DATASET.NUM_JOINTS += 1
+        cfg.MODEL.NUM_JOINTS = cfg.DATASET.NUM_JOINTS
+    cfg.TEST.IGNORE_CENTER = ignore_center
+    cfg.MODEL.TAG_PER_JOINT = tag_per_joint
+    return cfg
+
+
+def golden_glue_cfgs():
+    """get_multi_stage_outputs + aggregate_results of the unmodified reference for the cfg branches beyond the shipped
+    mobile.yaml: WITH_CENTER (kept / ignored) and TAG_PER_JOINT off; seeded fake model, inputs reproduced in the tests."""
+    ns = refshim.load()
+    for name, center, ignore, per_joint, proj, seed in GLUE_CFG_CASES:
+        cfg = glue_cfg(center, ignore, per_joint, proj)
+        jm = cfg.DATASET.NUM_JOINTS
+        fake = FakeScaleModel(jm, seed, None if per_joint else 1)
+        img = torch.zeros(2, 3, GLUE_CFG_SIZE, GLUE_CFG_SIZE)
+        _, h, t = ns.inference.get_multi_stage_outputs(cfg, fake, img, True, proj, (GLUE_CFG_SIZE, GLUE_CFG_SIZE))
+        fh, tl = ns.inference.aggregate_results(cfg, 1, None, [], h, t)
+        tags = torch.cat(tl, dim=4)
+        dig = hashlib.sha256(b"".join(o.numpy().tobytes() for outs in fake.log for o in outs)).hexdigest()
+        np.savez_compressed(os.path.join(OUT, "glue_cfg_%s.npz" % name), in_digest=np.array(dig),
+                            final_heatmaps=fh.numpy(), tags=tags.numpy())
 
 
 PARSER_CASES = [
@@ -270,12 +312,14 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "--new-r2":          # fixtures added in round 2 (others untouched)
         golden_parser_shared_tag()
         golden_glue_multiscale()
+        golden_glue_cfgs()
     else:
         golden_model()
         golden_glue()
         golden_parser()
         golden_parser_shared_tag()
         golden_glue_multiscale()
+        golden_glue_cfgs()
         golden_munkres()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

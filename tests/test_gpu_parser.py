@@ -284,7 +284,7 @@ def _glue_scales_device(cfg, log, base_wh, first_hw):
         keep.append((a, b))
         h, w = a[0].shape[2], a[0].shape[3]
         _lib.check(lib.lp_glue_scale_f32(a[0].data_ptr(), a[1].data_ptr(), _lib.ptr(b[0]), _lib.ptr(b[1]), fidx.data_ptr(),
-                                         n, J, h, w, 1 if flip else 0, Hd, Wd, 1 if i > 0 else 0,
+                                         n, J, J, 0, h, w, 1 if flip else 0, Hd, Wd, 1 if i > 0 else 0,
                                          float(len(scales)) if i == len(scales) - 1 else 1.0, det.data_ptr(),
                                          tag.data_ptr() if s == 1 else None, torch.cuda.current_stream().cuda_stream),
                    "lp_glue_scale_f32")
@@ -333,3 +333,32 @@ def test_glue_multiscale_ratios_vs_oracle(scales, proj, hw):
     assert det.shape == ed.shape and tag.shape == et.shape, (det.shape, ed.shape, smin)
     assert (det - ed).abs().max().item() <= 1e-5 * max(1.0, ed.abs().max().item())
     assert (tag - et).abs().max().item() <= 1e-5 * max(1.0, et.abs().max().item())
+
+
+def test_glue_cfg_branches_golden(golden_dir):
+    """DATASET.WITH_CENTER (centre joint kept / ignored) and MODEL.TAG_PER_JOINT off through lp_glue_scale_f32 against the
+    outputs of the unmodified reference (lib/core/inference.py:95-150)."""
+    from oracle.make_golden import GLUE_CFG_CASES, GLUE_CFG_SIZE, FakeScaleModel, glue_cfg
+    lib = _lib.load()
+    for name, center, ignore, per_joint, proj, seed in GLUE_CFG_CASES:
+        z = np.load(os.path.join(golden_dir, "glue_cfg_%s.npz" % name))
+        cfg = glue_cfg(center, ignore, per_joint, proj)
+        jm = cfg.DATASET.NUM_JOINTS
+        fake = FakeScaleModel(jm, seed, None if per_joint else 1)
+        img = torch.zeros(2, 3, GLUE_CFG_SIZE, GLUE_CFG_SIZE)
+        a, b = [t.cuda() for t in fake(img)], [t.cuda() for t in fake(img)]
+        dig = hashlib.sha256(b"".join(o.numpy().tobytes() for outs in fake.log for o in outs)).hexdigest()
+        assert dig == str(z["in_digest"])
+        ed, et = z["final_heatmaps"], z["tags"]
+        n, J, Hd, Wd = ed.shape
+        assert J == (jm - 1 if (center and ignore) else jm) and et.shape[1] == (J if per_joint else 1)
+        det = torch.full(ed.shape, float("nan"), device="cuda")
+        tag = torch.full(et.shape, float("nan"), device="cuda")
+        fidx = torch.tensor(flip_index_for(cfg), dtype=torch.int32, device="cuda")
+        h, w = a[0].shape[2], a[0].shape[3]
+        _lib.check(lib.lp_glue_scale_f32(a[0].data_ptr(), a[1].data_ptr(), b[0].data_ptr(), b[1].data_ptr(), fidx.data_ptr(),
+                                         n, J, jm, 0 if per_joint else 1, h, w, 1, Hd, Wd, 0, 1.0, det.data_ptr(),
+                                         tag.data_ptr(), torch.cuda.current_stream().cuda_stream), "lp_glue_scale_f32")
+        torch.cuda.synchronize()
+        assert np.abs(det.cpu().numpy() - ed).max() <= 1e-5 * max(1.0, np.abs(ed).max()), name
+        assert np.abs(tag.cpu().numpy() - et).max() <= 1e-5 * max(1.0, np.abs(et).max()), name

@@ -104,7 +104,10 @@ def test_unsupported_cfg_is_rejected():
     cfg = get_cfg(input_size=128)
     torch.manual_seed(0)
     model = get_pose_net(cfg, False, get_arch("XS")).eval().cuda()
-    for mutate in (lambda c: setattr(c.MODEL, "TAG_PER_JOINT", False), lambda c: setattr(c.DATASET, "WITH_CENTER", True),
+    def broken_reference_combo(c):                 # the reference drops the only tag map there (inference.py:147-150)
+        c.DATASET.WITH_CENTER, c.TEST.IGNORE_CENTER, c.MODEL.TAG_PER_JOINT = True, True, False
+
+    for mutate in (broken_reference_combo, lambda c: setattr(c.TEST, "WITH_HEATMAPS", (True, False)),
                    lambda c: setattr(c.TEST, "WITH_AE", (True, True))):
         c = get_cfg(input_size=128)
         mutate(c)
@@ -198,5 +201,53 @@ def test_multiscale_step_vs_oracle(scales, proj):
         ans, scores = op.parse(det_g[i:i + 1].copy(), tag_g[i:i + 1].copy(), True, True)
         e = np.asarray(ans[0], np.float32).reshape(-1, 14, 5)
         assert got[i][2] == e.shape[0] and e.shape[0] >= 3
+        assert np.array_equal(got[i][0], e), i
+        assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(scores, np.float32))
+
+
+@pytest.mark.parametrize("center,ignore,per_joint,dataset", [(True, True, True, "crowd_pose"), (True, False, True, "coco"),
+                                                             (False, True, False, "crowd_pose")])
+def test_step_cfg_branches_vs_oracle(center, ignore, per_joint, dataset):
+    """DATASET.WITH_CENTER (centre joint ignored / kept) and MODEL.TAG_PER_JOINT off, end to end: the network with the
+    matching head widths, the general glue entry and the parser, against the oracle (maps within the model tolerance,
+    keypoints bit-exactly the oracle parser's answer on the device's maps).  Heat peaks are planted, tags are the
+    network's own.  The kept centre joint is a COCO case: the reference's joint_order puts it at index 17
+    (group.py:113-118), which a 15-joint CrowdPose model does not have."""
+    from oracle import glue_ref, model_ref
+    from oracle.make_golden import glue_cfg
+    n, size = 2, 128
+    cfg = glue_cfg(center, ignore, per_joint, True, size=size, dataset=dataset)
+    arch = get_arch("XS")
+    torch.manual_seed(0)
+    model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, arch), 1)).eval()
+    sd = {k: v.float().clone() for k, v in model.state_dict().items()}
+    frames = synth.make_frames(n, size, seed=21)
+    pipe = LitePosePipeline(model.cuda(), cfg, use_graphs=True)
+    J = pipe.params.num_joints
+    assert J == {"crowd_pose": 14, "coco": 17}[dataset] + (1 if (center and not ignore) else 0)
+    plants = []
+    for dev in ("cuda", "cpu"):
+        pl = PlantedCrowd(n, J, size, size, 2, num_people=3, seed=12, device=dev)
+        pl.tidx, pl.tval = pl.tidx[:0], pl.tval[:0]          # heat peaks only
+        plants.append(pl)
+    got = pipe.step(frames.half().pin_memory(), plants[0])
+    st = pipe._get_state(n, size, size, torch.float16, plants[0])
+    det_g, tag_g = st["det"].cpu().numpy(), st["tag"].cpu().numpy()
+    with torch.no_grad():
+        _, hm, tg = glue_ref.multi_stage_outputs(cfg, lambda im: model_ref.forward(sd, arch, im), frames, True, True,
+                                                 (size, size))
+        det_o, tag_o = glue_ref.aggregate(cfg, hm, tg)
+        det_o, tag_o = det_o.contiguous(), tag_o.contiguous()
+        det_raw = det_o.clone()
+        plants[1].apply(det_o, tag_o)
+    assert det_g.shape == tuple(det_o.shape) and tag_g.shape == tuple(tag_o.shape)
+    assert tag_g.shape[1] == (J if per_joint else 1)
+    assert np.abs(det_g - det_o.numpy()).max() <= 2e-3 * np.abs(det_raw.numpy()).max() + 1e-4
+    assert np.abs(tag_g - tag_o.numpy()).max() <= 2e-3 * np.abs(tag_o.numpy()).max() + 1e-4
+    op = group_ref.HeatmapParser(cfg)
+    for i in range(n):
+        ans, scores = op.parse(det_g[i:i + 1].copy(), tag_g[i:i + 1].copy(), True, True)
+        e = np.asarray(ans[0], np.float32).reshape(-1, J, 5)
+        assert got[i][2] == e.shape[0] and e.shape[0] >= 1
         assert np.array_equal(got[i][0], e), i
         assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(scores, np.float32))

@@ -135,3 +135,26 @@ def test_parser_shared_tag(golden_dir):
         assert np.array_equal(np.array(scores, np.float32), z["scores_a%d_r0" % adj])
     ans, _ = p.parse(det[None].copy(), tag[None].copy(), True, True)      # the tiled-tag refine of the oracle runs
     assert np.array(ans[0]).shape[1:] == (14, 5)
+
+
+def _glue_cfg_inputs(z, case):
+    from oracle.make_golden import GLUE_CFG_SIZE, FakeScaleModel, glue_cfg
+    name, center, ignore, per_joint, proj, seed = case
+    cfg = glue_cfg(center, ignore, per_joint, proj)
+    fake = FakeScaleModel(cfg.DATASET.NUM_JOINTS, seed, None if per_joint else 1)
+    img = torch.zeros(2, 3, GLUE_CFG_SIZE, GLUE_CFG_SIZE)
+    return cfg, fake, img
+
+
+def test_glue_cfg_branches(golden_dir):
+    """WITH_CENTER (kept / ignored) and TAG_PER_JOINT off: oracle glue against the unmodified reference's outputs"""
+    from oracle.make_golden import GLUE_CFG_CASES, GLUE_CFG_SIZE
+    for case in GLUE_CFG_CASES:
+        z = np.load(os.path.join(golden_dir, "glue_cfg_%s.npz" % case[0]))
+        cfg, fake, img = _glue_cfg_inputs(z, case)
+        _, h, t = glue_ref.multi_stage_outputs(cfg, fake, img, True, case[4], (GLUE_CFG_SIZE, GLUE_CFG_SIZE))
+        fh, tg = glue_ref.aggregate(cfg, h, t)
+        dig = hashlib.sha256(b"".join(o.numpy().tobytes() for outs in fake.log for o in outs)).hexdigest()
+        assert dig == str(z["in_digest"])
+        assert np.allclose(fh.numpy(), z["final_heatmaps"], atol=2e-6), case[0]
+        assert np.allclose(tg.numpy(), z["tags"], atol=2e-6), case[0]
