@@ -551,6 +551,24 @@ def time_variants(args, model, x_dev, plant, device, iters=5):
         del pipe_full
     except Exception as e:
         out["from_uint8_images"] = {"error": str(e)[:200]}
+    # (d) multi-scale test (TEST.SCALE_FACTOR [0.5, 1, 2], valid.py:198-229): three network resolutions per frame, one
+    # accumulating glue launch per scale, the parser on the summed maps; batch 8 (the 2x scale is 1024^2)
+    try:
+        from litepose_b200 import synth
+        cfg_ms = get_cfg(input_size=S)
+        cfg_ms.TEST.SCALE_FACTOR = [0.5, 1, 2]
+        pipe_ms = LitePosePipeline(model, cfg_ms, use_graphs=True)
+        nb = min(B, 8)
+        xs = {s: synth.make_frames(nb, int(S * s), seed=31).half().to(device) for s in (0.5, 1.0, 2.0)}
+        plant_ms = PlantedCrowd(nb, 14, S, S, 2, num_people=args.people, seed=78, device=device)
+        tm = timed(lambda: pipe_ms.step_device_multiscale(xs, plant_ms), iters)
+        out["multiscale_test"] = {"frames_per_s": nb / tm, "ms_per_step": tm * 1e3, "batch": nb, "scales": [2, 1, 0.5],
+                                  "what": "TEST.SCALE_FACTOR [0.5,1,2] at base %dx%d: 6 network passes (%d^2, %d^2, %d^2) + 3 "
+                                          "accumulating glue launches + parser per frame, device resident, eager launches"
+                                          % (S, S, 2 * S, S, S // 2)}
+        del pipe_ms, xs
+    except Exception as e:
+        out["multiscale_test"] = {"error": str(e)[:200]}
     del pipe_fast
     torch.cuda.empty_cache()
     return out

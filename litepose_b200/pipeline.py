@@ -114,6 +114,10 @@ class LitePosePipeline(object):
         import os
         self.two_streams = os.environ.get("LP_TWO_STREAMS", "1") != "0"
         self.pair_batch = os.environ.get("LP_PAIR_BATCH", "0") == "1"      # experiment: both passes as one batch of 2N
+        # experiment: CUDA stream priorities of the kernels captured into the network graph / the glue+parser graph of
+        # the overlapped step (0 = default; negative = higher priority)
+        self.prio_net = int(os.environ.get("LP_PRIO_NET", "0"))
+        self.prio_parser = int(os.environ.get("LP_PRIO_PARSER", "0"))
         # persons per image in the fixed-size packed payload (the D2H copy / NCCL gather of every step).  The reference
         # returns every person it finds (lib/core/group.py:96,269-291); an image with more than ``keep`` persons is
         # never clipped: step() fetches the full result from the parser's buffers (capacity J*K persons) in a second
@@ -254,7 +258,10 @@ class LitePosePipeline(object):
         if ov is None:
             ov = st["ov"] = {"det": [st["det"], torch.empty_like(st["det"])], "tag": [st["tag"], torch.empty_like(st["tag"])],
                              "packed": [st["packed"], torch.zeros_like(st["packed"])], "gF": [None, None], "gP": [None, None],
-                             "pstream": torch.cuda.Stream(device=self.device), "P_done": [None, None],
+                             "pstream": torch.cuda.Stream(device=self.device, priority=self.prio_parser),
+                             "cap_net": torch.cuda.Stream(device=self.device, priority=self.prio_net),
+                             "cap_par": torch.cuda.Stream(device=self.device, priority=self.prio_parser),
+                             "P_done": [None, None],
                              "consumer_done": [None, None], "idx": 0}
         b = ov["idx"]
         ov["idx"] = b ^ 1
@@ -270,11 +277,11 @@ class LitePosePipeline(object):
             self._parser_part(st, ov["det"][b], ov["tag"][b], ov["packed"][b])
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=ov["cap_net"]):       # kernel nodes keep the capture stream's priority
                 o, f = self._network_part(st, st["x"], slot=b)
             ov["gF"][b] = g
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=ov["cap_par"]):
                 # the glue writes 1.4 GB at the HBM write roofline: on the second stream it overlaps the FMA-bound network
                 # passes of the next step (which write the other buffer set of the engine)
                 self._glue_part(st, o, f, ov["det"][b], ov["tag"][b])
@@ -308,7 +315,7 @@ class LitePosePipeline(object):
             row = J * (3 + T)
             st = {
                 "x": torch.empty((n, 3, s_h, s_w), dtype=dtype, device=dev),
-                "side": torch.cuda.Stream(device=dev),
+                "side": torch.cuda.Stream(device=dev, priority=self.prio_net),
                 "det": torch.empty((n, J, Hd, Wd), dtype=torch.float32, device=dev),
                 "tag": torch.empty((n, 1 if self.tag_shared else J, Hd, Wd, T), dtype=torch.float32, device=dev),
                 "packed": torch.zeros((n, self.keep * row + self.keep + 1), dtype=torch.float32, device=dev),

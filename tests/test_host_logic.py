@@ -2,6 +2,7 @@
 mirrors, drop-in module contract (state_dict keys, deepcopy, half wrapper on CPU), shard
 logic, and the world_size-2 gloo gather."""
 import copy
+import ctypes
 import os
 import re
 import socket
@@ -51,6 +52,53 @@ def test_host_side_packers_and_errors():
     # deconv program: 9 shifts per 64-channel block, 16 (phase, tap) weight tiles per block
     assert lib.lp_deconv_packed_elems(120, 48, 32) == (2 + 1) * 16 * 32 * 64
     assert lib.lp_nms_topk_workspace_bytes(2, 14, 512, 512, 30) == 2 * 14 * 8 * 8 * 30 * 8 + 2 * 14 * 8   # bands x warps lists + thresholds
+
+
+def test_round2_entry_points_validate_arguments():
+    """Argument errors of the entry points added in round 2 are reported before anything touches a device (no GPU here):
+    LP_ERR_BAD_ARG + a message naming the entry point."""
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)      # never dereferenced: the checks fail first
+    assert lib.lp_glue_scale_f32(None, one, None, None, None, 1, 14, 14, 0, 8, 8, 0, 16, 16, 0, 1.0, one, one, None) == 1
+    assert b"lp_glue_scale_f32" in lib.lp_last_error()
+    # model_joints < J, divide_by <= 0, a 10x shrink
+    assert lib.lp_glue_scale_f32(one, one, None, None, None, 1, 14, 13, 0, 8, 8, 0, 16, 16, 0, 1.0, one, one, None) == 1
+    assert b"model_joints" in lib.lp_last_error()
+    assert lib.lp_glue_scale_f32(one, one, None, None, None, 1, 14, 14, 0, 8, 8, 0, 16, 16, 1, 0.0, one, None, None) == 1
+    assert lib.lp_glue_scale_f32(one, one, None, None, None, 1, 14, 14, 0, 80, 80, 0, 16, 16, 0, 1.0, one, one, None) == 1
+    assert b"shrinks" in lib.lp_last_error()
+    assert lib.lp_glue_f32(one, one, None, None, None, 1, 14, 8, 8, 0, 16, 16, one, None, None) == 1      # tag required
+    assert lib.lp_pack_payload_f32(one, one, one, 2, 420, 70, 421, one, None) == 1                         # keep > pcap
+    assert b"lp_pack_payload_f32" in lib.lp_last_error()
+    assert lib.lp_plant_crowd_f32(one, None, None, 5, one, None, None, 0, None) == 1                        # list without data
+    assert lib.lp_plant_crowd_f32(one, None, None, 0, one, None, None, 0, None) == 0                        # nothing to plant
+    assert lib.lp_tag_match_f32(one, one, one, 1, 14, 65, 2, 64, one, 0.1, 1.0, 1, 0, 65, 14 * 65, one, one, one, 1 << 30,
+                                None) == 1
+    assert b"K<=64" in lib.lp_last_error()
+    assert lib.lp_tag_match_workspace_bytes(2, 14, 64, 2, 14 * 64) == 2 * 14 * 64 * (4 + 4 + 14 * 2 * 4)
+
+
+def test_pipeline_cfg_validation_is_host_side():
+    """LitePosePipeline._validate_cfg: what the fused glue covers and what it rejects (no GPU needed)."""
+    from litepose_b200.pipeline import LitePosePipeline
+    ok = get_cfg(input_size=128)
+    ok.TEST.SCALE_FACTOR = [2, 1, 0.5]
+    LitePosePipeline._validate_cfg(ok)
+    ok.DATASET.WITH_CENTER, ok.MODEL.TAG_PER_JOINT = True, True
+    LitePosePipeline._validate_cfg(ok)
+    for bad_scales in ([0.5, 2], [1, 1], [0, 1]):
+        c = get_cfg(input_size=128)
+        c.TEST.SCALE_FACTOR = bad_scales
+        with pytest.raises(ValueError):
+            LitePosePipeline._validate_cfg(c)
+    c = get_cfg(input_size=128)
+    c.DATASET.WITH_CENTER, c.TEST.IGNORE_CENTER, c.MODEL.TAG_PER_JOINT = True, True, False
+    with pytest.raises(NotImplementedError):
+        LitePosePipeline._validate_cfg(c)
+    c = get_cfg(input_size=128)
+    c.LOSS.NUM_STAGES = 3
+    with pytest.raises(NotImplementedError):
+        LitePosePipeline._validate_cfg(c)
 
 
 def test_config_mirrors_reference_values():

@@ -1,0 +1,42 @@
+"""Experiment: stream priorities of the network graph vs the glue+parser graph in the overlapped step
+(LP_PRIO_NET / LP_PRIO_PARSER).  Prints one JSON line per setting; CUDA-event timing, 5 warm-up + 30 timed steps."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from litepose_b200 import synth  # noqa: E402
+from litepose_b200.config import get_arch, get_cfg  # noqa: E402
+from litepose_b200.lib.models.pose_mobilenet import get_pose_net  # noqa: E402
+from litepose_b200.pipeline import LitePosePipeline, PlantedCrowd  # noqa: E402
+
+dev = torch.device("cuda", 0)
+cfg = get_cfg(input_size=512)
+torch.manual_seed(0)
+model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, get_arch("S")), 1)).eval().to(dev)
+x = synth.make_frames(32, 512, seed=1234).half().to(dev)
+plant = PlantedCrowd(32, 14, 512, 512, 2, num_people=5, seed=77, device=dev)
+lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+for net, par in ((0, 0), (-1, 0), (0, -1), (hi, 0), (0, hi), (0, 0)):
+    os.environ["LP_PRIO_NET"], os.environ["LP_PRIO_PARSER"] = str(net), str(par)
+    pipe = LitePosePipeline(model, cfg, use_graphs=True)
+    for _ in range(5):
+        pipe.step_device_overlapped(x, plant)
+    torch.cuda.synchronize()
+    best = None
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(30):
+            _, ev = pipe.step_device_overlapped(x, plant)
+        torch.cuda.current_stream().wait_event(ev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 30
+        best = ms if best is None else min(best, ms)
+    print(json.dumps({"prio_net": net, "prio_parser": par, "ms_per_step": best, "frames_per_s": 32e3 / best}), flush=True)
+    del pipe
