@@ -102,6 +102,13 @@ int num_sms() {
         cached = v;
         cached_dev = dev;
     }
+    // experiment knob: persistent kernels size their grids with fewer SMs (e.g. half the chip per pass of the flip test,
+    // so that the plain and the mirrored pass run side by side instead of alternating whole-chip kernels)
+    const char* e = getenv("LP_GRID_SMS");
+    if (e && e[0]) {
+        const int v = atoi(e);
+        if (v > 0 && v < cached) return v;
+    }
     return cached;
 }
 
