@@ -428,6 +428,42 @@ class LitePosePipeline(object):
         torch.cuda.current_stream().synchronize()
         return self.unpack(st["host"], st["row"], st["T"], self.fetch_overflow(st, st["host"]))
 
+    def infer_images(self, images, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), half=True, plant=None):
+        """The body of the reference's evaluation loop (valid.py:198-233) for a batch of equally sized uint8 images
+        [N,H,W,3] (host, ideally pinned, or device): get_multi_scale_size -> per scale of TEST.SCALE_FACTOR
+        resize_align_multi_scale + ToTensor + Normalize on the device (lp_warp_affine_normalize_u8) -> the network
+        passes, glue and parser of step() / step_multiscale() -> get_final_preds on the device.  Returns the list over
+        images of (final_results [P,J,3+T] in the coordinates of the original image, scores, P) - per image what
+        valid.py:227-233 holds in ``final_results`` and ``scores``."""
+        import numpy as np
+        from .lib.utils import transforms as T
+        if images.dim() != 4 or images.shape[3] != 3 or images.dtype != torch.uint8:
+            raise TypeError("infer_images: uint8 [N,H,W,3] expected")
+        n, h, w, _ = images.shape
+        size = int(self.cfg.DATASET.INPUT_SIZE)
+        smin = min(self.scales)
+        d = images.to(self.device, non_blocking=True)
+        xs, center, scale = {}, None, None
+        for s in self.scales:                     # the centre / scale valid.py hands to get_final_preds are the last scale's
+            xs[s], center, scale = T.resize_align_normalize_device(d, size, s, smin, list(mean), list(std), half=half)
+        self.set_final_preds([center] * n, [scale] * n)
+        try:
+            x1 = xs[1.0]
+            if len(self.scales) == 1:
+                packed = self.step_device(x1, plant)
+                det_hw = None
+            else:
+                packed = self.step_device_multiscale(xs, plant)
+                big = xs[self.scales[0]]
+                det_hw = (x1.shape[2], x1.shape[3]) if self.project else (big.shape[2] // 2, big.shape[3] // 2)
+            st = self._get_state(n, x1.shape[2], x1.shape[3], x1.dtype, plant, det_hw=det_hw)
+            self._last_state = st                 # det / tag of this call stay readable there until the next call
+            st["host"].copy_(packed, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return self.unpack(st["host"], st["row"], st["T"], self.fetch_overflow(st, st["host"]))
+        finally:
+            self.set_final_preds(None)
+
     # -- asynchronous end-to-end API: two steps in flight -----------------------------------------
     def submit(self, frames_pinned, plant=None, group=None, dst=0):
         """Enqueue one end-to-end step and return a ticket; ``collect(ticket)`` blocks until that step's keypoints are

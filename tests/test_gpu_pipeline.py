@@ -251,3 +251,57 @@ def test_step_cfg_branches_vs_oracle(center, ignore, per_joint, dataset):
         assert got[i][2] == e.shape[0] and e.shape[0] >= 1
         assert np.array_equal(got[i][0], e), i
         assert np.array_equal(np.asarray(got[i][1], np.float32), np.asarray(scores, np.float32))
+
+
+@pytest.mark.parametrize("scales", [[1], [0.5, 1, 2]])
+def test_infer_images_is_the_valid_loop_body(scales):
+    """LitePosePipeline.infer_images = valid.py:198-233 for a batch of uint8 images: per-scale warp + normalise on the
+    device, network passes, glue (accumulating over the scales), parser, get_final_preds.  Against the same chain built
+    from the separately pinned pieces: the device pre-processing (bit-identical to cv2 elsewhere), the oracle loop on
+    those frames (maps within the model tolerance), the oracle parser on the device's maps and the host get_final_preds
+    with the last scale's centre / scale (bit-exact final coordinates)."""
+    from litepose_b200.lib.utils import transforms as T
+    from oracle import glue_ref, model_ref
+    n, H, W, size = 2, 150, 200, 128
+    cfg = get_cfg(input_size=size)
+    cfg.TEST.SCALE_FACTOR = list(scales)
+    arch = get_arch("XS")
+    torch.manual_seed(0)
+    model = synth.scale_heads_(synth.randomize_bn_(get_pose_net(cfg, False, arch), 1)).eval()
+    sd = {k: v.float().clone() for k, v in model.state_dict().items()}
+    imgs = torch.from_numpy(np.random.RandomState(3).randint(0, 256, (n, H, W, 3)).astype(np.uint8))
+    smin = min(scales)
+    (bw, bh), _, _ = T.get_multi_scale_size(np.empty((H, W, 3), np.uint8), size, 1.0, smin)
+    pipe = LitePosePipeline(model.cuda(), cfg, use_graphs=True)
+    plant_dev = PlantedCrowd(n, 14, bh, bw, 2, num_people=3, seed=15, device="cuda")
+    plant_cpu = PlantedCrowd(n, 14, bh, bw, 2, num_people=3, seed=15, device="cpu")
+    got = pipe.infer_images(imgs.pin_memory(), plant=plant_dev)
+    got2 = pipe.infer_images(imgs.pin_memory(), plant=plant_dev)
+    # the pieces
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    frames, center, scale = {}, None, None
+    for s in sorted(scales, reverse=True):
+        x, center, scale = T.resize_align_normalize_device(imgs, size, s, smin, mean, std, half=True)
+        frames[float(s)] = x.float().cpu()
+    assert tuple(frames[1.0].shape[2:]) == (bh, bw)
+    st = pipe._last_state
+    det_g, tag_g = st["det"].cpu().numpy(), st["tag"].cpu().numpy()
+    with torch.no_grad():
+        fwd = lambda im: model_ref.forward(sd, arch, im)
+        if len(scales) > 1:
+            det_o, tag_o = glue_ref.multi_scale(cfg, fwd, frames, (bw, bh))
+        else:
+            _, hm, tg = glue_ref.multi_stage_outputs(cfg, fwd, frames[1.0], True, True, (bw, bh))
+            det_o, tag_o = glue_ref.aggregate(cfg, hm, tg)
+        det_o, tag_o = det_o.contiguous(), tag_o.contiguous()
+        lim_d, lim_t = 2e-3 * det_o.abs().max().item() + 1e-4, 2e-3 * tag_o.abs().max().item() + 1e-4
+        plant_cpu.apply(det_o, tag_o)
+    assert np.abs(det_g - det_o.numpy()).max() <= lim_d and np.abs(tag_g - tag_o.numpy()).max() <= lim_t
+    op = group_ref.HeatmapParser(cfg)
+    for i in range(n):
+        ans, scores = op.parse(det_g[i:i + 1].copy(), tag_g[i:i + 1].copy(), True, True)
+        exp = T.get_final_preds(ans, center, scale, [bw, bh])
+        for res in (got, got2):
+            assert res[i][2] == len(exp) and len(exp) >= 3
+            assert np.array_equal(res[i][0], np.stack(exp).astype(np.float32)), i
+            assert np.array_equal(np.asarray(res[i][1], np.float32), np.asarray(scores, np.float32))
