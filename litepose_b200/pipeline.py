@@ -73,6 +73,8 @@ class PlantedCrowd(object):
         if not self.didx.numel():
             return det, tag
         if det.is_cuda:
+            if not (det.is_contiguous() and tag.is_contiguous() and det.dtype == torch.float32 and tag.dtype == torch.float32):
+                raise ValueError("PlantedCrowd.apply: contiguous float32 det / tag expected")
             # one launch of the library's kernel (overlapping det patches: atomic max, order independent)
             _lib.check(_lib.load().lp_plant_crowd_f32(det.data_ptr(), self.didx.data_ptr(), self.dval.data_ptr(),
                                                       self.didx.numel(), tag.data_ptr(), self.tidx.data_ptr(),
