@@ -51,6 +51,15 @@ int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims
         set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
         return LP_ERR_CUDA;
     }
+    // cuTensorMapEncodeTiled is a DRIVER entry point: it needs a context current on the calling thread.  A thread that
+    // has not made a runtime call yet (an nn.DataParallel worker whose device is already the current one, so torch never
+    // calls cudaSetDevice in it) has none and the encode fails with CUDA_ERROR_INVALID_CONTEXT: bind the primary context
+    // of the current device once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     if (reinterpret_cast<uintptr_t>(base) & 15) {
         set_error("tensor map base address must be 16-byte aligned");
         return LP_ERR_ALIGN;
@@ -72,6 +81,11 @@ int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims
     }
     CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {       // e.g. the thread's context was popped by another library: bind and retry
+        cudaFree(nullptr);
+        r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]",
                   (int)r, rank, (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),

@@ -208,6 +208,35 @@ def test_pipeline_final_preds_on_device():
     assert all(np.array_equal(x[0], y[0]) for x, y in zip(plain, again))
 
 
+def test_forward_from_a_fresh_thread():
+    """nn.DataParallel (reference valid.py:165) calls forward from worker threads.  A thread that has made no CUDA
+    runtime call yet has no driver context bound, and the first entry point of the forward (the fused stem) builds a
+    tensor map through a driver call: the library binds the primary context itself.  One device is enough to see it."""
+    import threading
+    cfg = get_cfg(input_size=128)
+    torch.manual_seed(0)
+    model = synth.randomize_bn_(get_pose_net(cfg, False, get_arch("XS")), 1).cuda().eval()
+    x = synth.make_frames(2, 128, seed=3).cuda()
+    with torch.no_grad():
+        ref = model(x)                         # engine and plan are built here: the thread's first CUDA work is the library's
+    box = {}
+
+    def work():
+        try:
+            with torch.no_grad():
+                box["out"] = model(x)
+            torch.cuda.synchronize()
+        except Exception as e:                 # surfaced in the main thread below
+            box["err"] = e
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert "err" not in box, box.get("err")
+    for a, b in zip(ref, box["out"]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (nn.DataParallel over device_ids (0, 1))")
 def test_dataparallel_two_devices():
     """reference valid.py:165 wraps the model in nn.DataParallel: replicas run on threads and share the drop-in module's
