@@ -150,3 +150,82 @@ def flip_index_for(cfg):
     if cfg.DATASET.WITH_CENTER:
         name += "_WITH_CENTER"
     return FLIP_CONFIG[name]
+
+
+# ---- yacs-free loader for the reference's experiment files ------------------------------------------------------------
+# Defaults of the keys the inference path reads, as lib/config/default.py:20-153 sets them (the training / debug
+# sections of an experiment file are merged as they come: the reference's root node allows new keys).
+_DEFAULTS = {
+    "GPUS": (0,), "WORKERS": 4, "PRINT_FREQ": 20, "DATA_DIR": "", "OUTPUT_DIR": "", "LOG_DIR": "",
+    "FP16": {"ENABLED": False, "STATIC_LOSS_SCALE": 1.0, "DYNAMIC_LOSS_SCALE": False},
+    "CUDNN": {"BENCHMARK": True, "DETERMINISTIC": False, "ENABLED": True},
+    "MODEL": {"NAME": "pose_multi_resolution_net_v16", "INIT_WEIGHTS": True, "PRETRAINED": "", "NUM_JOINTS": 17,
+              "TAG_PER_JOINT": True, "EXTRA": {}, "SYNC_BN": False},
+    "LOSS": {"NUM_STAGES": 1, "WITH_HEATMAPS_LOSS": (True,), "HEATMAPS_LOSS_FACTOR": (1.0,), "WITH_AE_LOSS": (True,),
+             "AE_LOSS_TYPE": "max", "PUSH_LOSS_FACTOR": (0.001,), "PULL_LOSS_FACTOR": (0.001,)},
+    "DATASET": {"ROOT": "", "DATASET": "coco_kpt", "DATASET_TEST": "coco", "NUM_JOINTS": 17, "MAX_NUM_PEOPLE": 30,
+                "INPUT_SIZE": 512, "OUTPUT_SIZE": [128, 256, 512], "WITH_CENTER": False},
+    "TEST": {"IMAGES_PER_GPU": 32, "FLIP_TEST": False, "ADJUST": True, "REFINE": True, "SCALE_FACTOR": [1],
+             "DETECTION_THRESHOLD": 0.2, "TAG_THRESHOLD": 1.0, "USE_DETECTION_VAL": True, "IGNORE_TOO_MUCH": False,
+             "MODEL_FILE": "", "IGNORE_CENTER": True, "NMS_KERNEL": 3, "NMS_PADDING": 1, "PROJECT2IMAGE": False,
+             "WITH_HEATMAPS": (True,), "WITH_AE": (True,), "LOG_PROGRESS": False},
+}
+
+
+def _decode(v):
+    """yacs decodes string leaves with ast.literal_eval where that succeeds ("(True, False)" -> tuple, "1e-4" -> float)."""
+    import ast
+    if isinstance(v, dict):
+        return {k: _decode(x) for k, x in v.items()}
+    if isinstance(v, str):
+        try:
+            return ast.literal_eval(v)
+        except (ValueError, SyntaxError):
+            return v
+    return v
+
+
+def _merge(dst, src):
+    for k, v in src.items():
+        if isinstance(v, dict) and isinstance(dst.get(k), dict):
+            _merge(dst[k], v)
+        else:
+            dst[k] = copy.deepcopy(v)
+
+
+def load_experiment(yaml_path, superconfig=None, opts=()):
+    """What the reference's scripts do with ``--cfg FILE [--superconfig ARCH.json] [KEY VALUE ...]`` (valid.py:95-111,
+    lib/config/default.py:156-190), without yacs: defaults <- experiment file <- ``opts`` pairs, the WITH_CENTER joint
+    count adjustment, then the architecture's ``img_size`` as INPUT_SIZE / OUTPUT_SIZE.  Returns (cfg, cfg_arch);
+    cfg_arch is None without ``superconfig`` (a path, an arch name of get_arch, or a dict)."""
+    import yaml
+    tree = copy.deepcopy(_DEFAULTS)
+    with open(yaml_path, "r") as f:
+        _merge(tree, _decode(yaml.safe_load(f) or {}))
+    opts = list(opts)
+    if len(opts) % 2:
+        raise ValueError("opts must be KEY VALUE pairs")
+    for key, val in zip(opts[0::2], opts[1::2]):
+        node = tree
+        parts = key.split(".")
+        for p in parts[:-1]:
+            node = node[p]
+        if parts[-1] not in node:
+            raise KeyError("unknown config key %s" % key)
+        node[parts[-1]] = _decode(val)
+    ds, mdl, loss = tree["DATASET"], tree["MODEL"], tree["LOSS"]
+    if ds["WITH_CENTER"]:
+        ds["NUM_JOINTS"] += 1
+        mdl["NUM_JOINTS"] = ds["NUM_JOINTS"]
+    if not isinstance(ds["OUTPUT_SIZE"], (list, tuple)):
+        ds["OUTPUT_SIZE"] = [ds["OUTPUT_SIZE"]]
+    for k in ("WITH_HEATMAPS_LOSS", "HEATMAPS_LOSS_FACTOR"):
+        if not isinstance(loss[k], (list, tuple)):
+            loss[k] = (loss[k],)
+    arch = None
+    if superconfig is not None:
+        arch = get_arch(superconfig)
+        reso = int(arch["img_size"])
+        ds["INPUT_SIZE"] = reso
+        ds["OUTPUT_SIZE"] = [reso // 4, reso // 2]
+    return _cn(tree), arch

@@ -272,3 +272,66 @@ def test_dropin_install_refuses_late_binding(tmp_path):
             "try:\n    d.install()\nexcept ImportError as e:\n    print('refused', 'models' in str(e))\n" % (ROOT, str(tmp_path)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert "refused True" in r.stdout, r.stdout + r.stderr
+
+
+def test_load_experiment_without_yacs(tmp_path):
+    """config.load_experiment: the reference's --cfg / --superconfig / opts flow (valid.py:95-111) on an experiment file
+    in the reference's format; the evaluation keys equal get_cfg()'s literal table."""
+    from litepose_b200.config import load_experiment
+    text = """
+DATASET: {DATASET: crowd_pose_kpt, DATASET_TEST: crowd_pose, INPUT_SIZE: 256, OUTPUT_SIZE: [64, 128], MAX_NUM_PEOPLE: 30, NUM_JOINTS: 14}
+LOSS: {NUM_STAGES: 2, WITH_AE_LOSS: [True, False], WITH_HEATMAPS_LOSS: [True, True]}
+MODEL:
+  NAME: pose_mobilenet
+  NUM_JOINTS: 14
+  TAG_PER_JOINT: True
+  EXTRA: {FINAL_CONV_KERNEL: 1, NUM_DECONV_LAYERS: 3, NUM_DECONV_FILTERS: [64, 48, 32], NUM_DECONV_KERNELS: [4, 4, 4]}
+TEST:
+  FLIP_TEST: True
+  IMAGES_PER_GPU: 1
+  SCALE_FACTOR: [1]
+  DETECTION_THRESHOLD: 0.1
+  WITH_HEATMAPS: (True, True)
+  WITH_AE: (True, False)
+  PROJECT2IMAGE: True
+  NMS_KERNEL: 5
+  NMS_PADDING: 2
+TRAIN: {LR: 4e-3, WD: 1e-4}
+"""
+    path = tmp_path / "mobile.yaml"
+    path.write_text(text)
+    cfg, arch = load_experiment(str(path), superconfig="S")
+    ref = get_cfg(input_size=448)
+    assert arch["deconv_setting"] == [32, 24, 32] and cfg.DATASET.INPUT_SIZE == 448 and cfg.DATASET.OUTPUT_SIZE == [112, 224]
+    assert cfg.TEST.WITH_HEATMAPS == (True, True) and cfg.TEST.WITH_AE == (True, False) and cfg.TRAIN.WD == 1e-4
+    skip = {"INIT_WEIGHTS"}          # get_cfg() builds random-init models (no checkpoint in the synthetic setting)
+    for sec in ("MODEL", "LOSS", "DATASET", "TEST"):
+        for k, v in ref[sec].items():
+            if k in skip:
+                continue
+            got = cfg[sec][k]
+            if isinstance(v, (list, tuple)):
+                assert list(got) == list(v), (sec, k)
+            elif isinstance(v, dict):
+                assert dict(got) == dict(v), (sec, k)
+            else:
+                assert got == v, (sec, k, got, v)
+    # opts + the WITH_CENTER adjustment of update_config (lib/config/default.py:175-177)
+    cfg2, _ = load_experiment(str(path), opts=["DATASET.WITH_CENTER", "True", "TEST.SCALE_FACTOR", "[0.5, 1, 2]"])
+    assert cfg2.DATASET.NUM_JOINTS == 15 and cfg2.MODEL.NUM_JOINTS == 15 and cfg2.TEST.SCALE_FACTOR == [0.5, 1, 2]
+    with pytest.raises(KeyError):
+        load_experiment(str(path), opts=["TEST.NO_SUCH_KEY", "1"])
+    ref_yaml = "/root/reference/experiments/crowd_pose/mobilenet/mobile.yaml"
+    if os.path.exists(ref_yaml):               # the reference's own file (build container only)
+        cfg3, _ = load_experiment(ref_yaml, superconfig="S")
+        for sec in ("MODEL", "LOSS", "DATASET", "TEST"):
+            for k, v in ref[sec].items():
+                if k in skip:
+                    continue
+                got = cfg3[sec][k]
+                if isinstance(v, (list, tuple)):
+                    assert list(got) == list(v), (sec, k)
+                elif isinstance(v, dict):        # the file may carry more keys (PRETRAINED_LAYERS ...)
+                    assert all(list(got[k2]) == list(v2) if isinstance(v2, list) else got[k2] == v2 for k2, v2 in v.items()), (sec, k)
+                else:
+                    assert got == v, (sec, k)
