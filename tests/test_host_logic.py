@@ -335,3 +335,21 @@ TRAIN: {LR: 4e-3, WD: 1e-4}
                     assert all(list(got[k2]) == list(v2) if isinstance(v2, list) else got[k2] == v2 for k2, v2 in v.items()), (sec, k)
                 else:
                     assert got == v, (sec, k)
+
+
+def test_valid_synthetic_cli_dry_run(tmp_path):
+    """tools/valid_synthetic.py takes valid.py's arguments (--cfg, --superconfig, KEY VALUE opts) and resolves them as
+    valid.py:95-111 does; --dry-run stops before the first CUDA call."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("valid_synthetic", os.path.join(ROOT, "tools", "valid_synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    path = tmp_path / "exp.yaml"
+    path.write_text("DATASET: {DATASET: crowd_pose_kpt, DATASET_TEST: crowd_pose, NUM_JOINTS: 14}\n"
+                    "MODEL: {NAME: pose_mobilenet, NUM_JOINTS: 14, EXTRA: {NUM_DECONV_LAYERS: 3, NUM_DECONV_KERNELS: [4, 4, 4]}}\n"
+                    "LOSS: {NUM_STAGES: 2, WITH_AE_LOSS: [True, False], WITH_HEATMAPS_LOSS: [True, True]}\n"
+                    "TEST: {FLIP_TEST: True, WITH_HEATMAPS: (True, True), WITH_AE: (True, False), PROJECT2IMAGE: True}\n")
+    out = mod.main(["--cfg", str(path), "--superconfig", "XS", "--dry-run", "TEST.SCALE_FACTOR", "[0.5, 1]"])
+    assert out["input_size"] == 256 and out["scale_factor"] == [0.5, 1] and out["flip_test"] is True
+    with pytest.raises(ValueError):            # the reference needs the scale-1 pass (valid.py:224)
+        mod.main(["--cfg", str(path), "--superconfig", "XS", "--dry-run", "TEST.SCALE_FACTOR", "[0.5, 2]"])
