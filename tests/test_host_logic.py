@@ -348,7 +348,7 @@ def test_valid_synthetic_cli_dry_run(tmp_path):
     path.write_text("DATASET: {DATASET: crowd_pose_kpt, DATASET_TEST: crowd_pose, NUM_JOINTS: 14}\n"
                     "MODEL: {NAME: pose_mobilenet, NUM_JOINTS: 14, EXTRA: {NUM_DECONV_LAYERS: 3, NUM_DECONV_KERNELS: [4, 4, 4]}}\n"
                     "LOSS: {NUM_STAGES: 2, WITH_AE_LOSS: [True, False], WITH_HEATMAPS_LOSS: [True, True]}\n"
-                    "TEST: {FLIP_TEST: True, WITH_HEATMAPS: (True, True), WITH_AE: (True, False), PROJECT2IMAGE: True}\n")
+                    "TEST:\n  FLIP_TEST: True\n  WITH_HEATMAPS: (True, True)\n  WITH_AE: (True, False)\n  PROJECT2IMAGE: True\n")
     out = mod.main(["--cfg", str(path), "--superconfig", "XS", "--dry-run", "TEST.SCALE_FACTOR", "[0.5, 1]"])
     assert out["input_size"] == 256 and out["scale_factor"] == [0.5, 1] and out["flip_test"] is True
     with pytest.raises(ValueError):            # the reference needs the scale-1 pass (valid.py:224)
