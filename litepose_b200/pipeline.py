@@ -448,6 +448,7 @@ class LitePosePipeline(object):
         xs, center, scale = {}, None, None
         for s in self.scales:                     # the centre / scale valid.py hands to get_final_preds are the last scale's
             xs[s], center, scale = T.resize_align_normalize_device(d, size, s, smin, list(mean), list(std), half=half)
+        prev = self._final                     # a caller's own set_final_preds() setting is put back afterwards
         self.set_final_preds([center] * n, [scale] * n)
         try:
             x1 = xs[1.0]
@@ -464,7 +465,10 @@ class LitePosePipeline(object):
             torch.cuda.current_stream().synchronize()
             return self.unpack(st["host"], st["row"], st["T"], self.fetch_overflow(st, st["host"]))
         finally:
-            self.set_final_preds(None)
+            if prev is None:
+                self.set_final_preds(None)
+            else:
+                self.set_final_preds(prev[0], prev[1])
 
     # -- asynchronous end-to-end API: two steps in flight -----------------------------------------
     def submit(self, frames_pinned, plant=None, group=None, dst=0):
